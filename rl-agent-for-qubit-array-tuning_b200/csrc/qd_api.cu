@@ -1,0 +1,420 @@
+// qd_api.cu -- the C ABI of libqdsim.so (include/qdsim.h): context, model upload, launches.
+// No torch, no C++ types across the boundary; every entry point returns a qd_err.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "qd_kernels.cuh"
+
+static_assert(sizeof(qd_scan) == 480, "qd_scan must be 480 bytes (multiple of 16 for the TMA bulk copy)");
+static_assert(sizeof(qd_scan) % 16 == 0, "qd_scan size");
+
+struct qd_ctx {
+  int device = 0;
+  int sm_count = 0;
+  char err[512] = {0};
+  bool have_models = false;
+  qd_layout L{};
+  int n_env = 0;
+  double* d_records = nullptr;
+  size_t records_bytes = 0;
+  // staging for scan descriptors
+  qd_scan* d_scans = nullptr;
+  size_t scans_cap = 0;
+  qd_scan* h_scans = nullptr;   // pinned
+  size_t h_scans_cap = 0;
+  // scratch for the *_host entry points
+  float* d_z = nullptr;
+  size_t z_cap = 0;
+  void* d_n = nullptr;
+  size_t n_cap = 0;
+  double* d_pts = nullptr;
+  size_t pts_cap = 0;
+  cudaEvent_t staged = nullptr;   // h_scans may be rewritten once this has fired
+  int64_t launches = 0;
+};
+
+namespace {
+
+char g_err[512] = "no context";
+
+int fail(qd_ctx* ctx, int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(ctx ? ctx->err : g_err, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define QD_CUDA(ctx, call)                                                                      \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      return fail(ctx, QD_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+int grow(qd_ctx* ctx, T** p, size_t* cap, size_t need_bytes) {
+  if (*cap >= need_bytes) return QD_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t want = need_bytes + need_bytes / 4 + 256;
+  cudaError_t e = cudaMalloc((void**)p, want);
+  if (e != cudaSuccess) return fail(ctx, QD_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+  *cap = want;
+  return QD_OK;
+}
+
+size_t n_elem_size(int n_type) {
+  switch (n_type) {
+    case QD_N_U8: return 1;
+    case QD_N_F32: return 4;
+    case QD_N_F64: return 8;
+    default: return 0;
+  }
+}
+
+using kernel_fn = void (*)(const qd::KArgs);
+
+template <int ALG>
+kernel_fn pick_n(int n) {
+  switch (n) {
+    case 1: return qd::qd_scan_kernel<1, ALG>;
+    case 2: return qd::qd_scan_kernel<2, ALG>;
+    case 3: return qd::qd_scan_kernel<3, ALG>;
+    case 4: return qd::qd_scan_kernel<4, ALG>;
+    case 5: return qd::qd_scan_kernel<5, ALG>;
+    case 6: return qd::qd_scan_kernel<6, ALG>;
+    case 7: return qd::qd_scan_kernel<7, ALG>;
+    case 8: return qd::qd_scan_kernel<8, ALG>;
+    default: return nullptr;
+  }
+}
+
+kernel_fn pick_kernel(const qd_layout& L) {
+  if (L.algorithm == QD_ALG_BRUTE_FORCE) return pick_n<QD_ALG_BRUTE_FORCE>(L.n_dot);
+  if (L.algorithm == QD_ALG_DEFAULT || L.algorithm == QD_ALG_THRESHOLDED) return pick_n<QD_ALG_DEFAULT>(L.n_dot);
+  return nullptr;
+}
+
+int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) {
+  if (!ctx) return fail(nullptr, QD_ERR_INVALID, "ctx is NULL");
+  if (!ctx->have_models) return fail(ctx, QD_ERR_STATE, "qd_set_models has not been called");
+  if (n_type < QD_N_NONE || n_type > QD_N_F64) return fail(ctx, QD_ERR_INVALID, "bad n_type %d", n_type);
+  if (n_type != QD_N_NONE && !n_out) return fail(ctx, QD_ERR_INVALID, "n_out is NULL but n_type != QD_N_NONE");
+  if ((flags & QD_FLAG_THERMAL) && n_type == QD_N_U8)
+    return fail(ctx, QD_ERR_INVALID, "QD_FLAG_THERMAL yields non-integer occupations: use QD_N_F32/F64 or QD_N_NONE");
+  if ((flags & QD_FLAG_THERMAL) && (flags & QD_FLAG_LATCH) && (flags & QD_FLAG_LATCH_EXACT))
+    return fail(ctx, QD_ERR_UNSUPPORTED, "exact-compare latching of thermal (non-integer) occupations is not supported");
+  return QD_OK;
+}
+
+// enqueue one launch over device-resident descriptors
+int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const double* d_points, float* d_z, void* d_n,
+           int n_type, unsigned flags, cudaStream_t stream) {
+  kernel_fn fn = pick_kernel(ctx->L);
+  if (!fn) return fail(ctx, QD_ERR_UNSUPPORTED, "no kernel for n_dot=%d algorithm=%d", ctx->L.n_dot, ctx->L.algorithm);
+  qd::KArgs a;
+  a.L = ctx->L;
+  a.records = ctx->d_records;
+  a.scans = d_scans;
+  a.points = d_points;
+  a.z_out = d_z;
+  a.n_out = (n_type == QD_N_NONE) ? nullptr : d_n;
+  a.n_scan = n_scan;
+  a.n_type = n_type;
+  a.flags = flags;
+  a.slot_bytes = qd::qd_slot_bytes(ctx->L);
+  // item = block of rows of one scan handled by one warp.  Large batches: one scan per warp (staging amortised over
+  // the whole scan).  Small batches: split rows so that every SM gets work.  A flat (carry-rows) pass is sequential
+  // over the whole scan by definition.
+  const long long target_items = (long long)ctx->sm_count * 12 * 4;
+  long long rows = ((long long)n_scan * max_ny) / target_items;
+  if (rows < 1) rows = 1;
+  if (rows > max_ny) rows = max_ny;
+  if (flags & QD_FLAG_CARRY_ROWS) rows = max_ny;
+  a.rows_per_item = (int)rows;
+  a.items_per_scan = (max_ny + a.rows_per_item - 1) / a.rows_per_item;
+  const long long total_items = (long long)n_scan * a.items_per_scan;
+  const int wpc = (total_items < (long long)ctx->sm_count * 4) ? 1 : 4;
+  long long grid = (total_items + wpc - 1) / wpc;
+  if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+  const size_t smem = (size_t)a.slot_bytes * wpc;
+  if (smem > 48 * 1024)
+    QD_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fn<<<(unsigned)grid, wpc * 32, smem, stream>>>(a);
+  QD_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return QD_OK;
+}
+
+int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stream, int* max_ny) {
+  if (n_scan <= 0) return fail(ctx, QD_ERR_INVALID, "n_scan must be positive");
+  if (!scans) return fail(ctx, QD_ERR_INVALID, "scans is NULL");
+  int mny = 0;
+  for (int i = 0; i < n_scan; ++i) {
+    const qd_scan& s = scans[i];
+    if (s.env_id < 0 || s.env_id >= ctx->n_env)
+      return fail(ctx, QD_ERR_INVALID, "scan %d: env_id %d out of range [0,%d)", i, s.env_id, ctx->n_env);
+    if (s.nx <= 0 || s.ny <= 0) return fail(ctx, QD_ERR_INVALID, "scan %d: nx, ny must be positive", i);
+    if (s.pix_offset < 0) return fail(ctx, QD_ERR_INVALID, "scan %d: negative pix_offset", i);
+    if (s.ny > mny) mny = s.ny;
+  }
+  *max_ny = mny;
+  const size_t bytes = (size_t)n_scan * sizeof(qd_scan);
+  int rc = grow(ctx, &ctx->d_scans, &ctx->scans_cap, bytes);
+  if (rc) return rc;
+  QD_CUDA(ctx, cudaEventSynchronize(ctx->staged));   // the previous H2D out of the pinned buffer has finished
+  if (ctx->h_scans_cap < bytes) {
+    if (ctx->h_scans) cudaFreeHost(ctx->h_scans);
+    ctx->h_scans = nullptr;
+    ctx->h_scans_cap = 0;
+    const size_t want = bytes + bytes / 4 + 4096;
+    QD_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scans, want));
+    ctx->h_scans_cap = want;
+  }
+  memcpy(ctx->h_scans, scans, bytes);
+  QD_CUDA(ctx, cudaMemcpyAsync(ctx->d_scans, ctx->h_scans, bytes, cudaMemcpyHostToDevice, stream));
+  QD_CUDA(ctx, cudaEventRecord(ctx->staged, stream));
+  return QD_OK;
+}
+
+}  // namespace
+
+template <typename T>
+int measure_peak(qd_ctx* ctx, int iters, double* tflops) {
+  if (!ctx || !tflops) return fail(ctx, QD_ERR_INVALID, "NULL argument");
+  if (iters <= 0) iters = 4096;
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  T* d = nullptr;
+  QD_CUDA(ctx, cudaMalloc((void**)&d, sizeof(T) * blocks * threads));
+  cudaEvent_t e0, e1;
+  QD_CUDA(ctx, cudaEventCreate(&e0));
+  QD_CUDA(ctx, cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    QD_CUDA(ctx, cudaEventRecord(e0));
+    qd::qd_fma_peak_kernel<T><<<blocks, threads>>>(d, iters, (T)1.0000001, (T)1e-7);
+    QD_CUDA(ctx, cudaEventRecord(e1));
+    QD_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0.f;
+    QD_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) * 1e-12;
+    if (rep > 0 && tf > best) best = tf;
+    ctx->launches += 1;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *tflops = best;
+  return QD_OK;
+}
+
+extern "C" {
+
+int qd_abi_version(void) { return QD_ABI_VERSION; }
+
+int qd_create(int device, qd_ctx** out) {
+  if (!out) return fail(nullptr, QD_ERR_INVALID, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess) return fail(nullptr, QD_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(nullptr, QD_ERR_INVALID, "device %d out of range (have %d)", device, count);
+  qd_ctx* ctx = new (std::nothrow) qd_ctx();
+  if (!ctx) return fail(nullptr, QD_ERR_NOMEM, "out of host memory");
+  ctx->device = device;
+  e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->staged, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    fail(nullptr, QD_ERR_CUDA, "device %d init failed: %s", device, cudaGetErrorString(e));
+    delete ctx;
+    return QD_ERR_CUDA;
+  }
+  *out = ctx;
+  return QD_OK;
+}
+
+void qd_destroy(qd_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  if (ctx->d_records) cudaFree(ctx->d_records);
+  if (ctx->d_scans) cudaFree(ctx->d_scans);
+  if (ctx->h_scans) cudaFreeHost(ctx->h_scans);
+  if (ctx->d_z) cudaFree(ctx->d_z);
+  if (ctx->d_n) cudaFree(ctx->d_n);
+  if (ctx->d_pts) cudaFree(ctx->d_pts);
+  if (ctx->staged) cudaEventDestroy(ctx->staged);
+  delete ctx;
+}
+
+const char* qd_last_error(const qd_ctx* ctx) { return ctx ? ctx->err : g_err; }
+
+int64_t qd_launch_count(const qd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_gs, const double* cdd_gs,
+                  const double* cdd_inv_full, const double* cgd_full, const double* cbg, const qd_env_params* params) {
+  if (!ctx) return fail(nullptr, QD_ERR_INVALID, "ctx is NULL");
+  if (!desc || !cdd_inv_gs || !cdd_inv_full || !cgd_full || !params)
+    return fail(ctx, QD_ERR_INVALID, "NULL argument to qd_set_models");
+  const int N = desc->n_dot, NV = desc->n_volt, G = desc->n_gate, D = N + desc->n_sensor;
+  if (desc->n_env <= 0) return fail(ctx, QD_ERR_INVALID, "n_env must be positive");
+  if (N < 1 || N > QD_MAX_DOTS) return fail(ctx, QD_ERR_INVALID, "n_dot must be in 1..%d, got %d", QD_MAX_DOTS, N);
+  if (desc->n_sensor != 1) return fail(ctx, QD_ERR_UNSUPPORTED, "n_sensor must be 1, got %d", desc->n_sensor);
+  if (NV < 1 || NV > QD_MAX_VOLT || G < 1 || G > NV)
+    return fail(ctx, QD_ERR_INVALID, "bad n_volt=%d / n_gate=%d (max %d)", NV, G, QD_MAX_VOLT);
+  const int alg = desc->algorithm;
+  if (alg < QD_ALG_DEFAULT || alg > QD_ALG_TUNNEL) return fail(ctx, QD_ERR_INVALID, "Algorithm %d not supported", alg);
+  if (alg == QD_ALG_TUNNEL) return fail(ctx, QD_ERR_UNSUPPORTED, "QD_ALG_TUNNEL is not built yet");
+  if ((alg == QD_ALG_DEFAULT || alg == QD_ALG_THRESHOLDED) && !cdd_gs)
+    return fail(ctx, QD_ERR_INVALID, "cdd_gs is required for the default / thresholded algorithms");
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+
+  const qd_layout L = qd_make_layout(N, NV, G, alg, desc->num_charge_states, desc->charge_state_batch_size);
+  const size_t bytes = (size_t)desc->n_env * L.rec_doubles * sizeof(double);
+  std::vector<double> host;
+  try {
+    host.assign((size_t)desc->n_env * L.rec_doubles, 0.0);
+  } catch (...) {
+    return fail(ctx, QD_ERR_NOMEM, "out of host memory packing %d model records", desc->n_env);
+  }
+  for (int e = 0; e < desc->n_env; ++e) {
+    double* r = host.data() + (size_t)e * L.rec_doubles;
+    const qd_env_params& p = params[e];
+    if (alg == QD_ALG_BRUTE_FORCE && (p.max_charge_carriers < 0 || p.max_charge_carriers > 15))
+      return fail(ctx, QD_ERR_INVALID, "env %d: max_charge_carriers must be in 0..15", e);
+    if (!(p.kT >= 0.0)) return fail(ctx, QD_ERR_INVALID, "env %d: kT must be >= 0", e);
+    memcpy(r + L.o_cinv, cdd_inv_gs + (size_t)e * N * N, sizeof(double) * N * N);
+    if (cdd_gs) memcpy(r + L.o_cdd, cdd_gs + (size_t)e * N * N, sizeof(double) * N * N);
+    const double* cg = cgd_full + (size_t)e * D * NV;
+    memcpy(r + L.o_a, cg, sizeof(double) * N * NV);
+    memcpy(r + L.o_sa, cg + (size_t)N * NV, sizeof(double) * NV);
+    const double* ci = cdd_inv_full + (size_t)e * D * D;
+    for (int j = 0; j < N; ++j) r[L.o_sw + j] = ci[(size_t)N * D + j];
+    r[L.o_css] = ci[(size_t)N * D + N];
+    double* par = r + L.o_par;
+    par[QD_PAR_KT] = p.kT;
+    par[QD_PAR_THRESHOLD] = p.threshold;
+    par[QD_PAR_WHITE] = p.white_amp;
+    par[QD_PAR_P01] = p.tele_p01;
+    par[QD_PAR_P10] = p.tele_p10;
+    par[QD_PAR_TELE_AMP] = p.tele_amp;
+    const double tot = p.tele_p01 + p.tele_p10;
+    par[QD_PAR_TELE_STAT] = tot > 0.0 ? p.tele_p01 / tot : 0.0;
+    par[QD_PAR_LATCH] = p.latching ? 1.0 : 0.0;
+    par[QD_PAR_MAXC] = (double)p.max_charge_carriers;
+    par[QD_PAR_TC_BASE] = p.tc_base;
+    for (int j = 0; j < 8; ++j) r[L.o_alpha + j] = p.alpha[j];
+    for (int j = 0; j < 8; ++j) r[L.o_pleads + j] = p.p_leads[j];
+    for (int j = 0; j < 64; ++j) r[L.o_pinter + j] = p.p_inter[j];
+    if (alg == QD_ALG_TUNNEL && cbg)
+      memcpy(r + L.o_cbg, cbg + (size_t)e * (NV - G) * G, sizeof(double) * (NV - G) * G);
+  }
+  QD_CUDA(ctx, cudaDeviceSynchronize());   // nothing in flight may still read the old records
+  int rc = grow(ctx, &ctx->d_records, &ctx->records_bytes, bytes);
+  if (rc) return rc;
+  QD_CUDA(ctx, cudaMemcpy(ctx->d_records, host.data(), bytes, cudaMemcpyHostToDevice));
+  ctx->L = L;
+  ctx->n_env = desc->n_env;
+  if (alg == QD_ALG_DEFAULT || alg == QD_ALG_THRESHOLDED) {
+    const long long total = (long long)desc->n_env << N;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 65535) blocks = 65535;
+    qd::qd_build_q_kernel<<<(unsigned)blocks, 256>>>(L, ctx->d_records, desc->n_env);
+    QD_CUDA(ctx, cudaGetLastError());
+    QD_CUDA(ctx, cudaDeviceSynchronize());
+    ctx->launches += 1;
+  }
+  ctx->have_models = true;
+  return QD_OK;
+}
+
+int qd_scan_open(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_out, void* n_out, int n_type, unsigned flags,
+                 void* stream) {
+  int rc = validate_launch(ctx, n_type, flags, n_out);
+  if (rc) return rc;
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int max_ny = 0;
+  rc = stage_scans(ctx, n_scan, scans, (cudaStream_t)stream, &max_ny);
+  if (rc) return rc;
+  return launch(ctx, n_scan, ctx->d_scans, max_ny, nullptr, z_out, n_out, n_type, flags, (cudaStream_t)stream);
+}
+
+int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_out_host, void* n_out_host, int n_type,
+                      unsigned flags) {
+  int rc = validate_launch(ctx, n_type, flags, n_out_host);
+  if (rc) return rc;
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int max_ny = 0;
+  rc = stage_scans(ctx, n_scan, scans, nullptr, &max_ny);
+  if (rc) return rc;
+  long long pixels = 0;
+  for (int i = 0; i < n_scan; ++i) {
+    const long long end = scans[i].pix_offset + (long long)scans[i].nx * scans[i].ny;
+    if (end > pixels) pixels = end;
+  }
+  const int N = ctx->L.n_dot;
+  rc = grow(ctx, &ctx->d_z, &ctx->z_cap, (size_t)pixels * sizeof(float));
+  if (rc) return rc;
+  const size_t nbytes = (size_t)pixels * N * n_elem_size(n_type);
+  if (nbytes) {
+    rc = grow(ctx, (unsigned char**)&ctx->d_n, &ctx->n_cap, nbytes);
+    if (rc) return rc;
+  }
+  rc = launch(ctx, n_scan, ctx->d_scans, max_ny, nullptr, ctx->d_z, ctx->d_n, n_type, flags, nullptr);
+  if (rc) return rc;
+  if (z_out_host)
+    QD_CUDA(ctx, cudaMemcpyAsync(z_out_host, ctx->d_z, (size_t)pixels * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+  if (nbytes) QD_CUDA(ctx, cudaMemcpyAsync(n_out_host, ctx->d_n, nbytes, cudaMemcpyDeviceToHost, nullptr));
+  QD_CUDA(ctx, cudaStreamSynchronize(nullptr));
+  return QD_OK;
+}
+
+int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const double* v, float* z_out_host,
+                        void* n_out_host, int n_type, unsigned flags) {
+  int rc = validate_launch(ctx, n_type, flags, n_out_host);
+  if (rc) return rc;
+  if (!scan || !v) return fail(ctx, QD_ERR_INVALID, "NULL argument to qd_points_open_host");
+  if (nx <= 0 || ny <= 0) return fail(ctx, QD_ERR_INVALID, "nx, ny must be positive");
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  qd_scan s = *scan;
+  s.nx = nx;
+  s.ny = ny;
+  s.pix_offset = 0;
+  int max_ny = 0;
+  rc = stage_scans(ctx, 1, &s, nullptr, &max_ny);
+  if (rc) return rc;
+  const long long pixels = (long long)nx * ny;
+  const int N = ctx->L.n_dot, NV = ctx->L.n_volt;
+  rc = grow(ctx, &ctx->d_pts, &ctx->pts_cap, (size_t)pixels * NV * sizeof(double));
+  if (rc) return rc;
+  rc = grow(ctx, &ctx->d_z, &ctx->z_cap, (size_t)pixels * sizeof(float));
+  if (rc) return rc;
+  const size_t nbytes = (size_t)pixels * N * n_elem_size(n_type);
+  if (nbytes) {
+    rc = grow(ctx, (unsigned char**)&ctx->d_n, &ctx->n_cap, nbytes);
+    if (rc) return rc;
+  }
+  QD_CUDA(ctx, cudaMemcpyAsync(ctx->d_pts, v, (size_t)pixels * NV * sizeof(double), cudaMemcpyHostToDevice, nullptr));
+  rc = launch(ctx, 1, ctx->d_scans, max_ny, ctx->d_pts, ctx->d_z, ctx->d_n, n_type, flags, nullptr);
+  if (rc) return rc;
+  if (z_out_host)
+    QD_CUDA(ctx, cudaMemcpyAsync(z_out_host, ctx->d_z, (size_t)pixels * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+  if (nbytes) QD_CUDA(ctx, cudaMemcpyAsync(n_out_host, ctx->d_n, nbytes, cudaMemcpyDeviceToHost, nullptr));
+  QD_CUDA(ctx, cudaStreamSynchronize(nullptr));
+  return QD_OK;
+}
+
+int qd_measure_fp64_peak(qd_ctx* ctx, int iters, double* tflops) { return measure_peak<double>(ctx, iters, tflops); }
+int qd_measure_fp32_peak(qd_ctx* ctx, int iters, double* tflops) { return measure_peak<float>(ctx, iters, tflops); }
+
+}  // extern "C"

@@ -1,0 +1,640 @@
+// qd_kernels.cuh -- the per-pixel charge-stability kernels (Path A), hand-written for sm_100a.
+//
+// Work decomposition
+//   item  = (scan, block of rows).  One WARP owns one item at a time and is fully independent of the other warps of
+//           its CTA (no __syncthreads anywhere): it stages the env's model record and the scan descriptor into its own
+//           shared-memory slot with two TMA bulk copies on one mbarrier, derives the affine coefficients
+//           g(ix,iy) = g0 + ix*gx + iy*gy of the dot potentials (the voltage grid itself is never materialised), then
+//           walks its rows.  Within a row the 32 lanes take 32 consecutive pixels (fast axis x), so the fp32 sensor
+//           image and the uint8 charge map are written with fully coalesced 128 B / 32*N B warp stores.
+//   pixel = one thread: exact continuous relaxation (only when some dot potential is negative), floor, 2^N candidate
+//           search, then -- cooperatively across the warp, sequential along x -- hysteresis latching and the
+//           telegraph-noise chain, then the sensor Lorentzians and the noise terms.
+//
+// Candidate search without the O(N^2) quadratic form per candidate.  With r = floor(n_c) - g and h = Cinv r,
+//     E(delta) = (r+delta)^T Cinv (r+delta) = r.h + sum_j delta_j 2 h_j + Q[delta],   Q[delta] = delta^T Cinv delta.
+//   Q depends on the env only: 2^N doubles precomputed at qd_set_models and staged with the record.  The linear part
+//   splits over the low/high halves of the bit string: L(delta) = Lhi[H] + Llo[b]; Llo (<=16 values) lives in
+//   registers.  Per candidate the inner loop is one broadcast LDS (shared by two candidates), one DADD and one
+//   compare/select; per H one more DADD + compare.  Enumeration order = ascending index, dot 0 most significant,
+//   strict '<' so the first minimum wins (oracle/path_a.py).
+#pragma once
+#include <math.h>
+
+#include "qd_device.cuh"
+#include "qd_layout.h"
+
+namespace qd {
+
+struct KArgs {
+  qd_layout L;
+  const double* __restrict__ records;
+  const qd_scan* __restrict__ scans;
+  const double* __restrict__ points;   // [pixels, n_volt] or nullptr (affine scans)
+  float* __restrict__ z_out;
+  void* __restrict__ n_out;
+  int n_scan;
+  int n_type;
+  unsigned flags;
+  int rows_per_item;
+  int items_per_scan;
+  int slot_bytes;
+};
+
+constexpr int QD_DER_DOUBLES = 48;  // derived per-item block: g0[8] gx[8] gy[8] us0 usx usy pad[5] carry[8] + spare
+
+__host__ __device__ inline int qd_slot_bytes(const qd_layout& L) {
+  int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_DER_DOUBLES * 8 + 16;
+  return (b + 127) & ~127;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Exact continuous relaxation: min (n-g)^T cdd^{-1} (n-g), n >= 0  (monotone active set on the M-matrix cdd).
+// oracle/path_a.py: continuous_relaxation.
+// ---------------------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __restrict__ cdd, double (&nc)[N]) {
+  unsigned act = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) act |= (g[j] < 0.0) ? (1u << j) : 0u;
+  double w[N];
+#pragma unroll 1
+  for (int round = 0; round <= N; ++round) {
+    double m[N * (N + 1) / 2];
+    double y[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const bool ai = (act >> i) & 1u;
+      y[i] = ai ? -g[i] : 0.0;
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        const bool both = ai && ((act >> j) & 1u);
+        m[i * (i + 1) / 2 + j] = both ? cdd[i * N + j] : (i == j ? 1.0 : 0.0);
+      }
+    }
+    // LDL^T in place (SPD, no pivoting); forward substitution fused
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double inv = 1.0 / m[k * (k + 1) / 2 + k];
+      m[k * (k + 1) / 2 + k] = inv;
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) {
+        const double u = m[i * (i + 1) / 2 + k];
+        const double l = u * inv;
+#pragma unroll
+        for (int j = k + 1; j < i; ++j) m[i * (i + 1) / 2 + j] -= u * m[j * (j + 1) / 2 + k];
+        m[i * (i + 1) / 2 + i] -= u * l;
+        y[i] -= l * y[k];
+        m[i * (i + 1) / 2 + k] = l;
+      }
+    }
+    double mu[N];
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+      double s = y[k] * m[k * (k + 1) / 2 + k];
+#pragma unroll
+      for (int i = k + 1; i < N; ++i) s -= m[i * (i + 1) / 2 + k] * mu[i];
+      mu[k] = s;
+    }
+    unsigned neu = act;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s = g[i];
+#pragma unroll
+      for (int j = 0; j < N; ++j) s = fma(cdd[i * N + j], mu[j], s);
+      s = ((act >> i) & 1u) ? 0.0 : s;
+      w[i] = s;
+      neu |= (s < 0.0) ? (1u << i) : 0u;
+    }
+    const bool changed = neu != act;
+    act = neu;
+    if (!__any_sync(0xffffffffu, changed)) break;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) nc[j] = fmax(w[j], 0.0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// default / thresholded ground state of one pixel.  nd[] <- occupations (integers when kT == 0).
+// ---------------------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void ground_state_box(const double (&g)[N], const double* __restrict__ rec,
+                                                 const qd_layout& L, bool thresholded, double kT, double (&nd)[N]) {
+  constexpr int NLO = N < 4 ? N : 4;
+  constexpr int NHI = N - NLO;
+  constexpr int LOC = 1 << NLO;
+  const double* __restrict__ cinv = rec + L.o_cinv;
+  const double* __restrict__ Q = rec + L.o_q;
+
+  bool neg = false;
+#pragma unroll
+  for (int j = 0; j < N; ++j) neg |= g[j] < 0.0;
+  double nc[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) nc[j] = g[j];
+  if (__any_sync(0xffffffffu, neg)) relax_lcp<N>(g, rec + L.o_cdd, nc);
+
+  double f[N], r[N], lin[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    f[j] = floor(nc[j]);
+    r[j] = f[j] - g[j];
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) s = fma(cinv[i * N + j], r[j], s);
+    lin[i] = 2.0 * s;
+  }
+  // thresholded: dots that keep only round(n_c).  bit (N-1-j) <-> dot j
+  unsigned fixmask = 0, fixval = 0;
+  if (thresholded) {
+    const double half_thr = 0.5 * rec[L.o_par + QD_PAR_THRESHOLD];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const double frac = nc[j] - f[j];
+      if (!(fabs(frac - 0.5) < half_thr)) {
+        fixmask |= 1u << (N - 1 - j);
+        if (floor(nc[j] + 0.5) - f[j] == 1.0) fixval |= 1u << (N - 1 - j);
+      }
+    }
+  }
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  double llo[LOC];
+  llo[0] = 0.0;
+#pragma unroll
+  for (int p = 0; p < NLO; ++p)
+#pragma unroll
+    for (int b = 0; b < (1 << p); ++b) llo[b + (1 << p)] = llo[b] + lin[N - 1 - p];
+  if (thresholded) {
+#pragma unroll
+    for (int b = 0; b < LOC; ++b)
+      if (((unsigned)b ^ fixval) & fixmask & (LOC - 1)) llo[b] = INF;
+  }
+
+  double best = INF;
+  int bidx = 0;
+#pragma unroll 1
+  for (int H = 0; H < (1 << NHI); ++H) {
+    double lh = 0.0;
+#pragma unroll
+    for (int p = 0; p < NHI; ++p) lh += ((H >> p) & 1) ? lin[N - 1 - NLO - p] : 0.0;
+    if (thresholded && ((((unsigned)H << NLO) ^ fixval) & fixmask & ~(unsigned)(LOC - 1))) lh = INF;
+    const double* __restrict__ q = Q + (H << NLO);
+    double m = INF;
+    int mb = 0;
+#pragma unroll
+    for (int b = 0; b < LOC; ++b) {
+      const double e = llo[b] + q[b];
+      if (e < m) { m = e; mb = b; }
+    }
+    const double e = m + lh;
+    if (e < best) { best = e; bidx = (H << NLO) | mb; }
+  }
+
+  if (kT > 0.0) {
+    // Boltzmann average over the same candidates, weights exp(-(E - Emin)/kT)
+    const double inv_kT = 1.0 / kT;
+    double Z = 0.0;
+    double acc[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) acc[j] = 0.0;
+#pragma unroll 1
+    for (int H = 0; H < (1 << NHI); ++H) {
+      double lh = 0.0;
+#pragma unroll
+      for (int p = 0; p < NHI; ++p) lh += ((H >> p) & 1) ? lin[N - 1 - NLO - p] : 0.0;
+      if (thresholded && ((((unsigned)H << NLO) ^ fixval) & fixmask & ~(unsigned)(LOC - 1))) continue;
+      const double* __restrict__ q = Q + (H << NLO);
+      double wh = 0.0;
+#pragma unroll
+      for (int b = 0; b < LOC; ++b) {
+        const double d = ((llo[b] + q[b]) + lh - best) * inv_kT;
+        if (d < 40.0) {
+          const double wgt = exp(-d);
+          wh += wgt;
+#pragma unroll
+          for (int p = 0; p < NLO; ++p)
+            if ((b >> p) & 1) acc[N - 1 - p] += wgt;
+        }
+      }
+      Z += wh;
+#pragma unroll
+      for (int p = 0; p < NHI; ++p)
+        if ((H >> p) & 1) acc[N - 1 - NLO - p] += wh;
+    }
+    const double invZ = 1.0 / Z;
+#pragma unroll
+    for (int j = 0; j < N; ++j) nd[j] = f[j] + acc[j] * invZ;
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) nd[j] = f[j] + (double)((bidx >> (N - 1 - j)) & 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// brute_force ground state: all n in {0..maxc}^N, dot 0 slowest.  Level-recursive evaluation: with r = n - g,
+//   E_l = E_{l-1} + r_l (Cinv_ll r_l + t_l),   t_k (k > l) += 2 Cinv_kl r_l
+// so the innermost dot costs 2 FMA + compare per candidate.
+// ---------------------------------------------------------------------------------------------------------------
+template <int N, int LVL>
+struct BruteLevel {
+  // PASS 0: argmin.  PASS 1: Boltzmann accumulation against `best`.
+  template <int PASS>
+  static __device__ __forceinline__ void run(const double* __restrict__ cinv, const double (&g)[N], int maxc, double e_prev,
+                                             double (&t)[N], unsigned code, double& best, unsigned& bcode,
+                                             double inv_kT, double& Z, double (&acc)[N]) {
+    const double cll = cinv[LVL * N + LVL];
+#pragma unroll 1
+    for (int v = 0; v <= maxc; ++v) {
+      const double rl = (double)v - g[LVL];
+      const double e = fma(rl, fma(cll, rl, t[LVL]), e_prev);
+      const unsigned c2 = code * 16u + (unsigned)v;
+      if constexpr (LVL == N - 1) {
+        if constexpr (PASS == 0) {
+          if (e < best) { best = e; bcode = c2; }
+        } else {
+          const double d = (e - best) * inv_kT;
+          if (d < 40.0) {
+            const double wgt = exp(-d);
+            Z += wgt;
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[j] += wgt * (double)((c2 >> (4 * (N - 1 - j))) & 15u);
+          }
+        }
+      } else {
+        double t2[N];
+#pragma unroll
+        for (int k = 0; k < N; ++k) t2[k] = (k > LVL) ? fma(2.0 * cinv[k * N + LVL], rl, t[k]) : 0.0;
+        BruteLevel<N, LVL + 1>::template run<PASS>(cinv, g, maxc, e, t2, c2, best, bcode, inv_kT, Z, acc);
+      }
+    }
+  }
+};
+template <int N>
+struct BruteLevel<N, N> {
+  template <int PASS>
+  static __device__ __forceinline__ void run(const double*, const double (&)[N], int, double, double (&)[N], unsigned,
+                                             double&, unsigned&, double, double&, double (&)[N]) {}
+};
+
+template <int N>
+__device__ __forceinline__ void ground_state_brute(const double (&g)[N], const double* __restrict__ rec,
+                                                   const qd_layout& L, double kT, double (&nd)[N]) {
+  const double* __restrict__ cinv = rec + L.o_cinv;
+  const int maxc = (int)rec[L.o_par + QD_PAR_MAXC];
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  double best = INF, Z = 0.0;
+  unsigned bcode = 0;
+  double t[N], acc[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) { t[j] = 0.0; acc[j] = 0.0; }
+  BruteLevel<N, 0>::template run<0>(cinv, g, maxc, 0.0, t, 0u, best, bcode, 0.0, Z, acc);
+  if (kT > 0.0) {
+    BruteLevel<N, 0>::template run<1>(cinv, g, maxc, 0.0, t, 0u, best, bcode, 1.0 / kT, Z, acc);
+    const double invZ = 1.0 / Z;
+#pragma unroll
+    for (int j = 0; j < N; ++j) nd[j] = acc[j] * invZ;
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) nd[j] = (double)((bcode >> (4 * (N - 1 - j))) & 15u);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The scan kernel.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t compose2(uint32_t later, uint32_t earlier) {
+  // functions {0,1}->{0,1} encoded as bit s = f(s); returns later o earlier
+  return ((later >> (earlier & 1u)) & 1u) | (((later >> ((earlier >> 1) & 1u)) & 1u) << 1);
+}
+
+template <int N>
+__device__ __forceinline__ uint64_t pack_key(const double (&nd)[N]) {
+  uint64_t k = 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) k |= (uint64_t)((unsigned)(int)floor(nd[j] + 0.5) & 0xffu) << (8 * j);
+  return k;
+}
+
+template <int N, int ALG>
+__global__ void __launch_bounds__(128, 3) qd_scan_kernel(const KArgs a) {
+  extern __shared__ __align__(128) unsigned char qd_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const qd_layout& L = a.L;
+  const int NV = L.n_volt;
+
+  unsigned char* slot = qd_smem + (size_t)warp * a.slot_bytes;
+  double* rec = reinterpret_cast<double*>(slot);
+  qd_scan* sc = reinterpret_cast<qd_scan*>(slot + (size_t)L.rec_doubles * 8);
+  double* der = reinterpret_cast<double*>(slot + (size_t)L.rec_doubles * 8 + sizeof(qd_scan));
+  uint64_t* bar = reinterpret_cast<uint64_t*>(der + QD_DER_DOUBLES);
+  double* d_g0 = der;
+  double* d_gx = der + 8;
+  double* d_gy = der + 16;
+  double* d_us = der + 24;      // us0, usx, usy
+  double* d_carry = der + 32;   // latched configuration of the last pixel of the previous chunk
+
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  uint32_t phase = 0;
+
+  const bool f_latch = a.flags & QD_FLAG_LATCH;
+  const bool f_noise = a.flags & QD_FLAG_NOISE;
+  const bool f_radial = a.flags & QD_FLAG_RADIAL;
+  const bool f_thermal = a.flags & QD_FLAG_THERMAL;
+  const bool f_carry = a.flags & QD_FLAG_CARRY_ROWS;
+  const bool f_white_out = a.flags & QD_FLAG_WHITE_ON_OUTPUT;
+  const uint32_t rec_bytes = (uint32_t)L.rec_doubles * 8u;
+
+  const long long total_items = (long long)a.n_scan * a.items_per_scan;
+  for (long long item = (long long)blockIdx.x * warps_per_cta + warp; item < total_items;
+       item += (long long)gridDim.x * warps_per_cta) {
+    const int scan_id = (int)(item / a.items_per_scan);
+    const int part = (int)(item - (long long)scan_id * a.items_per_scan);
+    const qd_scan* gscan = a.scans + scan_id;
+
+    // ---- stage record + scan descriptor (TMA bulk, one mbarrier) ----
+    if (lane == 0) {
+      const int env = gscan->env_id;
+      fence_proxy_async();
+      mbar_expect_tx(bar, rec_bytes + (uint32_t)sizeof(qd_scan));
+      tma_bulk_g2s(rec, a.records + (size_t)env * L.rec_doubles, rec_bytes, bar);
+      tma_bulk_g2s(sc, gscan, (uint32_t)sizeof(qd_scan), bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+
+    const int nx = sc->nx, ny = sc->ny;
+    const int row0 = part * a.rows_per_item;
+    const int row1 = min(ny, row0 + a.rows_per_item);
+    if (row0 >= ny) { __syncwarp(); continue; }
+
+    // ---- affine coefficients of the dot potentials and of the sensor potential ----
+    if (a.points == nullptr) {
+      if (lane <= N) {
+        const double* arow = (lane < N) ? rec + L.o_a + lane * NV : rec + L.o_sa;
+        double s0 = 0.0, sx = 0.0, sy = 0.0;
+        for (int k = 0; k < NV; ++k) {
+          const double c = arow[k];
+          s0 = fma(c, sc->v0[k], s0);
+          sx = fma(c, sc->dx[k], sx);
+          sy = fma(c, sc->dy[k], sy);
+        }
+        if (lane < N) { d_g0[lane] = s0; d_gx[lane] = sx; d_gy[lane] = sy; }
+        else { d_us[0] = s0; d_us[1] = sx; d_us[2] = sy; }
+      }
+    }
+    __syncwarp();
+
+    const double* par = rec + L.o_par;
+    const double kT = f_thermal ? par[QD_PAR_KT] : 0.0;
+    const bool latch_on = f_latch && par[QD_PAR_LATCH] != 0.0;
+    const bool replace = f_radial && sc->rad_mode == 2;
+    const uint64_t seed = sc->seed;
+    const long long pix0 = sc->pix_offset;
+    const double inv_gamma = 1.0 / sc->peak_width;
+    const double css = rec[L.o_css];
+    const bool need_rng = f_noise || latch_on || (f_radial && sc->rad_mode != 0);
+
+    uint64_t held_key = 0;
+    bool have_held = false;
+    uint32_t tele_state = 0;
+    bool tele_init = false;
+
+    for (int iy = row0; iy < row1; ++iy) {
+      if (!f_carry) { have_held = false; tele_init = false; }
+      for (int c0 = 0; c0 < nx; c0 += 32) {
+        const int ix = c0 + lane;
+        const bool valid = ix < nx;
+        const int ixc = valid ? ix : nx - 1;
+        const long long pix = (long long)iy * nx + ixc;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+
+        // ---- random draws of this pixel ----
+        float z_white = 0.f, z_rad = 0.f, u_latch = 0.f, u_tele = 0.f;
+        if (need_rng) {
+          const Philox4 w = philox4x32_10(seed, (uint64_t)pix, 0u);
+          box_muller(w.w0, w.w1, z_white, z_rad);
+          u_latch = u24(w.w2);
+          u_tele = u24(w.w3);
+        }
+
+        double nd[N];
+        double g[N];
+        double us;
+        float zf;
+        if (!replace) {
+          // ---- dot potentials g = cgd . v ----
+          if (a.points == nullptr) {
+            const double fx = (double)ixc, fy = (double)iy;
+#pragma unroll
+            for (int j = 0; j < N; ++j) g[j] = fma(fy, d_gy[j], fma(fx, d_gx[j], d_g0[j]));
+            us = fma(fy, d_us[2], fma(fx, d_us[1], d_us[0]));
+          } else {
+            const double* __restrict__ v = a.points + (size_t)pix * NV;
+#pragma unroll
+            for (int j = 0; j < N; ++j) g[j] = 0.0;
+            us = 0.0;
+            for (int k = 0; k < NV; ++k) {
+              const double vk = v[k];
+#pragma unroll
+              for (int j = 0; j < N; ++j) g[j] = fma(rec[L.o_a + j * NV + k], vk, g[j]);
+              us = fma(rec[L.o_sa + k], vk, us);
+            }
+          }
+
+          // ---- ground state ----
+          if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N>(g, rec, L, kT, nd);
+          else ground_state_box<N>(g, rec, L, L.algorithm == QD_ALG_THRESHOLDED, kT, nd);
+
+          // ---- hysteresis latching along x ----
+          if (latch_on) {
+            uint64_t key = pack_key<N>(nd);
+            unsigned todo = vmask;
+            if (!have_held) {                       // first pixel of the row (or of the scan): accepted as is
+              held_key = shfl_u64(key, 0);
+              todo &= ~1u;
+              have_held = true;
+            }
+            while (true) {
+              const unsigned diff = __ballot_sync(0xffffffffu, key != held_key) & todo;
+              if (!diff) break;
+              const int i = __ffs(diff) - 1;
+              const uint64_t ck = shfl_u64(key, i);
+              const float u = __shfl_sync(0xffffffffu, u_latch, i);
+              const uint64_t x = ck ^ held_key;
+              const uint64_t nz = (((x & 0x7f7f7f7f7f7f7f7fULL) + 0x7f7f7f7f7f7f7f7fULL) | x) & 0x8080808080808080ULL;
+              const int ndiff = __popcll(nz);
+              bool accept = true;
+              if (ndiff == 1) {
+                const int d0 = (__ffsll((long long)nz) - 1) >> 3;
+                accept = (double)u < rec[L.o_pleads + d0];
+              } else if (ndiff == 2) {
+                const int d0 = (__ffsll((long long)nz) - 1) >> 3;
+                const int d1 = (63 - __clzll((long long)nz)) >> 3;
+                accept = (double)u < rec[L.o_pinter + d0 * 8 + d1];
+              }
+              if (accept) {
+                held_key = ck;
+              } else {
+                // pixel i keeps the configuration of the pixel before it
+                const int src = (i > 0) ? i - 1 : 0;
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                  const double prev = shfl_f64(nd[j], src);
+                  const double held = (i > 0) ? prev : d_carry[j];
+                  if (lane == i) nd[j] = held;
+                }
+                if (lane == i) key = held_key;
+              }
+              todo &= ~((2u << i) - 1u);
+            }
+            // configuration after the last valid pixel -> carry for the next chunk
+            const int last = 31 - __clz(vmask);
+            if (lane == last) {
+#pragma unroll
+              for (int j = 0; j < N; ++j) d_carry[j] = nd[j];
+            }
+            __syncwarp();
+          }
+
+          // ---- sensor input noise: white + telegraph ----
+          double noise_in = 0.0, noise_out = 0.0;
+          if (f_noise) {
+            const double wn = par[QD_PAR_WHITE] * (double)z_white;
+            if (f_white_out) noise_out = wn; else noise_in = wn;
+            const double tamp = par[QD_PAR_TELE_AMP];
+            if (tamp != 0.0) {
+              if (!tele_init) {
+                if (f_carry) tele_state = 0u;
+                else {
+                  const Philox4 wr = philox4x32_10(seed, (uint64_t)iy, 1u);
+                  tele_state = ((double)u24(wr.w0) < par[QD_PAR_TELE_STAT]) ? 1u : 0u;
+                }
+                tele_init = true;
+              }
+              const uint32_t flip0 = ((double)u_tele < par[QD_PAR_P01]) ? 1u : 0u;
+              const uint32_t flip1 = ((double)u_tele < par[QD_PAR_P10]) ? 1u : 0u;
+              uint32_t fn = valid ? ((0u ^ flip0) | ((1u ^ flip1) << 1)) : 2u;   // invalid lanes: identity
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t other = __shfl_up_sync(0xffffffffu, fn, d);
+                if (lane >= d) fn = compose2(fn, other);
+              }
+              const uint32_t st = (fn >> tele_state) & 1u;
+              tele_state = __shfl_sync(0xffffffffu, st, 31);
+              noise_in += tamp * (double)st;
+            }
+          }
+
+          // ---- sensor: ten Lorentzians of the first differences of the full-system free energy ----
+          double base = 0.0;
+#pragma unroll
+          for (int j = 0; j < N; ++j) base = fma(rec[L.o_sw + j], nd[j] - g[j], base);
+          base *= 2.0;
+          const double t = (rint(us) + noise_in) - us;
+          float zs = 0.f;
+#pragma unroll
+          for (int k = -5; k < 5; ++k) {
+            const double dphi = fma(css, 2.0 * (t + (double)k) + 1.0, base);
+            const float xk = (float)(dphi * inv_gamma);
+            zs += 1.0f / fmaf(xk, xk, 1.0f);
+          }
+          double z = (double)zs + noise_out;
+          if (f_radial && sc->rad_mode == 1) {
+            const double vx = fma((double)ixc, sc->rad_dx, sc->rad_x0);
+            const double vy = fma((double)iy, sc->rad_dy, sc->rad_y0);
+            const double dist = sqrt(vx * vx + vy * vy);
+            const double amp = fmin(fmax(sc->rad_alpha * (dist - sc->rad_zero_radius), 0.0), sc->rad_max_amp);
+            z = fma((double)z_rad, amp, z);
+          }
+          zf = (float)z;
+        } else {
+          zf = z_rad;
+#pragma unroll
+          for (int j = 0; j < N; ++j) nd[j] = 0.0;
+        }
+
+        // ---- coalesced stores ----
+        if (valid) {
+          const long long o = pix0 + (long long)iy * nx + ix;
+          if (a.z_out) a.z_out[o] = zf;
+          if (a.n_type == QD_N_U8) {
+            unsigned char* p = reinterpret_cast<unsigned char*>(a.n_out) + o * N;
+            if constexpr (N == 8) {
+              uint64_t k = 0;
+#pragma unroll
+              for (int j = 0; j < N; ++j) k |= (uint64_t)(unsigned char)min(255, (int)nd[j]) << (8 * j);
+              *reinterpret_cast<uint64_t*>(p) = k;
+            } else if constexpr (N == 4) {
+              uint32_t k = 0;
+#pragma unroll
+              for (int j = 0; j < N; ++j) k |= (uint32_t)(unsigned char)min(255, (int)nd[j]) << (8 * j);
+              *reinterpret_cast<uint32_t*>(p) = k;
+            } else if constexpr (N == 2) {
+              const uint16_t k = (uint16_t)((unsigned char)min(255, (int)nd[0]) | ((unsigned char)min(255, (int)nd[1]) << 8));
+              *reinterpret_cast<uint16_t*>(p) = k;
+            } else {
+#pragma unroll
+              for (int j = 0; j < N; ++j) p[j] = (unsigned char)min(255, (int)nd[j]);
+            }
+          } else if (a.n_type == QD_N_F32) {
+            float* p = reinterpret_cast<float*>(a.n_out) + o * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) p[j] = (float)nd[j];
+          } else if (a.n_type == QD_N_F64) {
+            double* p = reinterpret_cast<double*>(a.n_out) + o * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) p[j] = nd[j];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Setup kernel: Q[delta] = delta^T Cinv delta for every env (once per qd_set_models).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void qd_build_q_kernel(qd_layout L, double* __restrict__ records, int n_env) {
+  const int n = L.n_dot;
+  const int per = 1 << n;
+  const long long total = (long long)n_env * per;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int env = (int)(t / per);
+    const unsigned idx = (unsigned)(t - (long long)env * per);
+    double* rec = records + (size_t)env * L.rec_doubles;
+    const double* cinv = rec + L.o_cinv;
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) {
+      if (!((idx >> (n - 1 - i)) & 1u)) continue;
+      for (int j = 0; j < n; ++j)
+        if ((idx >> (n - 1 - j)) & 1u) s += cinv[i * n + j];
+    }
+    rec[L.o_q + idx] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FMA micro-benchmarks: the roofline denominators of this FP-pipe-bound path (MEASURED_PEAKS.json has no CUDA-core
+// figure).  8 independent chains per thread.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) qd_fma_peak_kernel(T* out, int iters, T a, T b) {
+  T x0 = (T)threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = x0 * a + b; x1 = x1 * a + b; x2 = x2 * a + b; x3 = x3 * a + b;
+      x4 = x4 * a + b; x5 = x5 * a + b; x6 = x6 * a + b; x7 = x7 * a + b;
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace qd

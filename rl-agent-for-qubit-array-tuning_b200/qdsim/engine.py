@@ -1,0 +1,190 @@
+"""Host engine: one ``Engine`` per (process, GPU) wrapping a ``qd_ctx`` of libqdsim.so.
+
+This is the batched entry point (thousands of independent env.step calls per launch).  The reference-compatible
+single-device classes (``qarray.ChargeSensedDotArray`` ...) sit on top of it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib, maxwell
+from ._lib import (ALGORITHMS, FLAG_CARRY_ROWS, FLAG_LATCH, FLAG_LATCH_EXACT, FLAG_NOISE, FLAG_RADIAL,  # noqa: F401
+                   FLAG_THERMAL, FLAG_WHITE_ON_OUTPUT, N_DTYPES, N_F32, N_F64, N_NONE, N_U8, PARAMS_DTYPE,
+                   QD_MAX_DOTS, QD_MAX_VOLT, SCAN_DTYPE, QdError)
+
+K_B = 8.617333262145e-5  # eV/K (src/qarray_latched/DotArrays/_helper_functions.py:213-214)
+
+
+@dataclass
+class ModelBatch:
+    """Per-env constants of ``n_env`` devices in Maxwell form (fp64), as uploaded by ``qd_set_models``."""
+    algorithm: str
+    n_gate: int
+    cdd_inv_gs: np.ndarray            # (E, N, N)
+    cdd_gs: np.ndarray | None         # (E, N, N)
+    cdd_inv_full: np.ndarray          # (E, D, D)
+    cgd_full: np.ndarray              # (E, D, NV)
+    params: np.ndarray                # (E,) PARAMS_DTYPE
+    cbg: np.ndarray | None = None     # (E, B, G)
+    num_charge_states: int = 32
+    charge_state_batch_size: int = 1000
+
+    @property
+    def n_env(self) -> int:
+        return self.cdd_inv_gs.shape[0]
+
+    @property
+    def n_dot(self) -> int:
+        return self.cdd_inv_gs.shape[-1]
+
+    @property
+    def n_volt(self) -> int:
+        return self.cgd_full.shape[-1]
+
+    @classmethod
+    def from_capacitances(cls, Cdd, Cgd, Cds, Cgs, algorithm: str = "default", T=0.0, threshold=1.0,
+                          max_charge_carriers: int = 4, p_leads=None, p_inter=None, white_amp=0.0, tele_p01=0.0,
+                          tele_p10=0.0, tele_amp=0.0) -> "ModelBatch":
+        """Path A (``ChargeSensedDotArray``) batch from non-Maxwell matrices with a leading env axis.
+
+        The dots' ground state uses the dot-only Maxwell matrices, the sensor the full [dots, sensor] system
+        (TunnelCoupledChargeSensed.py:117-130 keeps both sets).
+        """
+        Cdd = np.asarray(Cdd, dtype=np.float64)
+        Cgd = np.asarray(Cgd, dtype=np.float64)
+        Cds = np.asarray(Cds, dtype=np.float64)
+        Cgs = np.asarray(Cgs, dtype=np.float64)
+        if Cdd.ndim == 2:
+            Cdd, Cgd, Cds, Cgs = Cdd[None], Cgd[None], Cds[None], Cgs[None]
+        n_env, n_dot = Cdd.shape[0], Cdd.shape[-1]
+        cdd, cdd_inv, _ = maxwell.maxwell(Cdd, Cgd)
+        cdd_full_nm, cgd_full_nm = maxwell.embed_sensor(Cdd, Cgd, Cds, Cgs)
+        _, cdd_inv_full, cgd_full = maxwell.maxwell(cdd_full_nm, cgd_full_nm)
+        params = np.zeros(n_env, dtype=PARAMS_DTYPE)
+        params["kT"] = K_B * np.broadcast_to(np.asarray(T, dtype=np.float64), (n_env,))
+        params["threshold"] = threshold
+        params["max_charge_carriers"] = max_charge_carriers
+        params["white_amp"] = white_amp
+        params["tele_p01"] = tele_p01
+        params["tele_p10"] = tele_p10
+        params["tele_amp"] = tele_amp
+        if p_leads is not None:
+            pl = np.broadcast_to(np.asarray(p_leads, dtype=np.float64), (n_env, n_dot))
+            pi = np.broadcast_to(np.asarray(p_inter, dtype=np.float64), (n_env, n_dot, n_dot))
+            params["latching"] = 1
+            params["p_leads"][:, :n_dot] = pl
+            pin = np.zeros((n_env, QD_MAX_DOTS, QD_MAX_DOTS))
+            pin[:, :n_dot, :n_dot] = pi
+            params["p_inter"] = pin.reshape(n_env, -1)
+        return cls(algorithm=algorithm, n_gate=Cgd.shape[-1], cdd_inv_gs=cdd_inv, cdd_gs=cdd,
+                   cdd_inv_full=cdd_inv_full, cgd_full=cgd_full, params=params)
+
+
+def new_scans(n: int) -> np.ndarray:
+    """Zero-initialised array of ``n`` scan descriptors (``qd_scan``)."""
+    s = np.zeros(n, dtype=SCAN_DTYPE)
+    s["peak_width"] = 1.0
+    return s
+
+
+def _ptr(a) -> int | None:
+    """Device / host pointer of a torch tensor, numpy array, int or None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+class Engine:
+    """One ``qd_ctx``: owns the device-resident model records of its env shard.  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        rc = self._lib.qd_create(int(device), C.byref(self._ctx))
+        if rc != 0:
+            raise QdError(rc, self._lib.qd_last_error(None).decode())
+        self.device = int(device)
+        self.models: ModelBatch | None = None
+
+    # -- lifecycle -------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.qd_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise QdError(rc, self._lib.qd_last_error(self._ctx).decode())
+
+    # -- models ----------------------------------------------------------------------------------------------
+    def set_models(self, mb: ModelBatch):
+        alg = ALGORITHMS.get(mb.algorithm.lower())
+        if alg is None:
+            raise AssertionError(f"Algorithm {mb.algorithm} not supported")
+        d = mb.cdd_inv_full.shape[-1]
+        desc = _lib.ModelDesc(mb.n_env, mb.n_dot, d - mb.n_dot, mb.n_volt, mb.n_gate, alg, mb.num_charge_states,
+                              mb.charge_state_batch_size or 0)
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None
+                for a in (mb.cdd_inv_gs, mb.cdd_gs, mb.cdd_inv_full, mb.cgd_full, mb.cbg)]
+        params = np.ascontiguousarray(mb.params, dtype=PARAMS_DTYPE)
+        self._check(self._lib.qd_set_models(self._ctx, C.byref(desc), *[_ptr(a) for a in arrs], _ptr(params)))
+        self.models = mb
+
+    # -- launches --------------------------------------------------------------------------------------------
+    def scan_open(self, scans: np.ndarray, z_out, n_out=None, n_type: int = N_NONE, flags: int = 0, stream=None):
+        """Asynchronous batched launch into DEVICE buffers (torch tensors or raw pointers)."""
+        assert scans.dtype == SCAN_DTYPE and scans.flags.c_contiguous
+        sp = None if stream is None else (stream if isinstance(stream, int) else stream.cuda_stream)
+        self._check(self._lib.qd_scan_open(self._ctx, len(scans), _ptr(scans), _ptr(z_out), _ptr(n_out), n_type,
+                                           flags, sp))
+
+    def scan_open_host(self, scans: np.ndarray, n_type: int = N_U8, flags: int = 0, want_z: bool = True):
+        """Synchronous launch returning host arrays ``(z float32 [pixels], n [pixels, N] or None)``."""
+        assert scans.dtype == SCAN_DTYPE and scans.flags.c_contiguous
+        pixels = int((scans["pix_offset"] + scans["nx"].astype(np.int64) * scans["ny"]).max())
+        z = np.empty(pixels, dtype=np.float32) if want_z else None
+        n = np.empty((pixels, self.models.n_dot), dtype=N_DTYPES[n_type]) if n_type != N_NONE else None
+        self._check(self._lib.qd_scan_open_host(self._ctx, len(scans), _ptr(scans), _ptr(z), _ptr(n), n_type, flags))
+        return z, n
+
+    def points_open_host(self, scan: np.ndarray, v: np.ndarray, n_type: int = N_F64, flags: int = 0,
+                         want_z: bool = True):
+        """Arbitrary voltage list ``v`` (ny, nx, n_volt) -> ``(z (ny, nx) float32, n (ny, nx, N))``."""
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        ny, nx, nv = v.shape
+        if nv != self.models.n_volt:
+            raise ValueError(f"The shape of vg is in correct it should be of shape (..., n_gate) = (...,{self.models.n_volt})")
+        scan = np.ascontiguousarray(scan, dtype=SCAN_DTYPE).reshape(1)
+        z = np.empty((ny, nx), dtype=np.float32) if want_z else None
+        n = np.empty((ny, nx, self.models.n_dot), dtype=N_DTYPES[n_type]) if n_type != N_NONE else None
+        self._check(self._lib.qd_points_open_host(self._ctx, _ptr(scan), ny, nx, _ptr(v), _ptr(z), _ptr(n), n_type,
+                                                  flags))
+        return z, n
+
+    # -- introspection ---------------------------------------------------------------------------------------
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.qd_launch_count(self._ctx))
+
+    def fp64_peak_tflops(self, iters: int = 4096) -> float:
+        out = C.c_double()
+        self._check(self._lib.qd_measure_fp64_peak(self._ctx, iters, C.byref(out)))
+        return out.value
+
+    def fp32_peak_tflops(self, iters: int = 4096) -> float:
+        out = C.c_double()
+        self._check(self._lib.qd_measure_fp32_peak(self._ctx, iters, C.byref(out)))
+        return out.value
