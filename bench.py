@@ -1,0 +1,350 @@
+#!/usr/bin/env python
+"""bench.py -- ground-state pixels/s and env steps/s of the charge-stability hot path (BASELINE.json metric).
+
+A "step" is one pass of the hot path over one batch of env.step calls: for every env, the N-1 adjacent-pair scan
+windows (res x res pixels each) through ground-state solve -> latching -> sensor -> noise.  Workload at N GPUs:
+BASELINE config 4 -- 8-dot latched array, 16384 envs PER GPU (weak scaling: envs shard by contiguous env id, no
+collective on the step path), 64x64 scans, full sensor-noise model.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Prints ONE JSON line on rank 0.  `value` = pixels/s with descriptors and models resident in HBM; `e2e` = the same
+through the host-buffer path (descriptors H2D from pinned memory + sensor images D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "rl-agent-for-qubit-array-tuning_b200")
+for _p in (ROOT, PKG, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Algorithmic work per pixel (DESIGN.md "Roofline").  SURVEY.md 8d counts the reference formulation (every candidate a
+# full N^2 quadratic form); the kernel evaluates the same argmin through the factorisation
+#   E(delta) = r.h + sum_j delta_j 2h_j + Q[delta],  Q precomputed per env,
+# whose fp64 work is what the FP64 pipe actually has to do.  Both are reported.
+# ---------------------------------------------------------------------------------------------------------------
+def flops_reference_formulation(n: int) -> float:
+    g, d = n + 1, n + 1
+    return 2.0 * (n * g + (2 ** n) * n * (n + 1) + d * g + 11 * d * (d + 1)) + 60
+
+
+def flops_factored(n: int) -> float:
+    """fp64 operations of the factored search, FMA = 2 flop, add / compare = 1 flop, no relaxation."""
+    nlo = min(n, 4)
+    nhi = n - nlo
+    pot = 2 * (2 * n) + 4                    # g = g0 + ix gx + iy gy, sensor potential
+    lin = n + 2 * n * n + n                  # r = f - g, h = Cinv r, 2h
+    llo = (1 << nlo) - 1
+    search = (1 << nhi) * (nhi + 2 * (1 << nlo) + 2)
+    sensor = 3 * n + 8 + 10 * 4
+    return float(pot + lin + llo + search + sensor)
+
+
+def fp64_pipe_ops_factored(n: int) -> float:
+    """fp64-pipe instruction slots per pixel (FMA, add, compare each occupy one slot)."""
+    nlo = min(n, 4)
+    nhi = n - nlo
+    return float(2 * n + 2 + n + n * n + n + ((1 << nlo) - 1) + (1 << nhi) * (nhi + 2 * (1 << nlo) + 2) + 2 * n + 8 + 20)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except OSError:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the restated reference path on the host cores (oracle/), bounded sample of the same workload.
+# ---------------------------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+    mb_fields, rec, flags = job
+    from util import oracle_batch
+    from qdsim.engine import ModelBatch
+    mb = ModelBatch(**mb_fields)
+    oracle_batch(mb, rec, flags)
+    return int(rec["nx"][0]) * int(rec["ny"][0]) * len(rec)
+
+
+def cpu_reference_pixels_per_s(mb, scans, flags, n_sample_scans: int, cores: int):
+    """Pixels/s of the CPU restatement over ``n_sample_scans`` scans of the workload using ``cores`` processes."""
+    import multiprocessing as mp
+    try:
+        from oracle import cport
+        if cport.available():
+            return cport.time_scans(mb, scans[:n_sample_scans], flags, threads=cores) + ("port (C restatement, OpenMP)",)
+    except ImportError:
+        pass
+    sample = scans[:n_sample_scans]
+    envs = np.unique(sample["env_id"])
+    remap = {int(e): i for i, e in enumerate(envs)}
+    fields = dict(algorithm=mb.algorithm, n_gate=mb.n_gate, cdd_inv_gs=mb.cdd_inv_gs[envs], cdd_gs=mb.cdd_gs[envs],
+                  cdd_inv_full=mb.cdd_inv_full[envs], cgd_full=mb.cgd_full[envs], params=mb.params[envs])
+    sample = sample.copy()
+    sample["env_id"] = [remap[int(e)] for e in sample["env_id"]]
+    jobs = [(fields, sample[i:i + 1], flags) for i in range(len(sample))]
+    ctx = mp.get_context("fork")
+    t0 = time.perf_counter()
+    with ctx.Pool(cores) as pool:
+        pixels = sum(pool.map(_cpu_worker, jobs, chunksize=1))
+    dt = time.perf_counter() - t0
+    return pixels / dt, pixels, dt, "port (NumPy restatement, one process per core)"
+
+
+def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int):
+    from qdsim import synth
+    dev = synth.sample_devices(n_env, n_dot, seed=1234 + rank)
+    mb = synth.model_batch(dev, algorithm="default", thermal=False, latching=True, noise=True)
+    sets = [synth.env_step_scans(mb, dev, res=res, seed=99 + rank, step=s) for s in range(n_sets)]
+    return dev, mb, sets
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-env", type=int, default=16384, help="envs per GPU")
+    ap.add_argument("--n-dot", type=int, default=8)
+    ap.add_argument("--res", type=int, default=64)
+    ap.add_argument("--cpu-scans", type=int, default=0, help="scans in the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_NONE, N_U8
+    flags = FLAG_LATCH | FLAG_NOISE | FLAG_RADIAL
+    N, res = args.n_dot, args.res
+    pix_per_env = (N - 1) * res * res
+    workload = (f"{N}-dot latched array, {args.n_env} envs/GPU, {N - 1} scans/env of {res}x{res}, default algorithm, "
+                f"T=0, latching + white/telegraph/radial noise")
+    config = {"workload": workload, "n_dot": N, "n_env_per_gpu": args.n_env, "res": res,
+              "scans_per_env": N - 1, "l2": "inputs+outputs per step >> L2 (outputs alone 12 B/pixel)"}
+
+    # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cores = os.cpu_count() or 1
+        n_scans = args.cpu_scans or max(cores, 16)
+        n_env_s = max(1, (n_scans + N - 2) // (N - 1))
+        dev, mb, sets = build_workload(n_env_s, N, res, 0, 1)
+        per_step = []
+        kind = ""
+        for _ in range(args.warmup + args.steps):
+            pps, pixels, dt, kind = cpu_reference_pixels_per_s(mb, sets[0], flags, n_scans, cores)
+            per_step.append((pixels, dt))
+        timed = per_step[args.warmup:]
+        pixels = sum(p for p, _ in timed)
+        dt = sum(t for _, t in timed)
+        value = pixels / dt
+        sample = f"{n_scans} scans ({timed[0][0]} pixels) of the workload per step"
+        print(json.dumps({
+            "impl": "reference", "metric": "ground_state_pixels_per_s", "value": value, "unit": "pixels/s",
+            "env_steps_per_s": value / pix_per_env, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / max(1, len(timed)), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "pixels/s", "cores": cores, "kind": "port", "sample": sample,
+                             "what": kind},
+            "e2e": {"value": value, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    from qdsim import Engine
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = Engine(local_rank)
+    n_sets = 2
+    dev, mb, sets = build_workload(args.n_env, N, res, rank, n_sets)
+    eng.set_models(mb)
+    n_scan = len(sets[0])
+    pixels = n_scan * res * res
+    stream = torch.cuda.current_stream()
+    z_dev = torch.empty(pixels, dtype=torch.float32, device="cuda")
+    n_dev = torch.empty((pixels, N), dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident timing: `value` and the kernel's roofline ----
+    eng.scan_upload(sets[0], stream)
+    for _ in range(warmup):
+        eng.scan_launch(z_dev, n_dev, N_U8, flags, stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record(stream)
+    for k in range(args.steps):
+        eng.scan_launch(z_dev, n_dev, N_U8, flags, stream)
+        ev[k + 1].record(stream)
+    barrier()
+    launches = eng.launch_count - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
+    ms_per_step = total_ms / args.steps
+    value = world * pixels / (ms_per_step * 1e-3)
+    checksum = int(n_dev[:: max(1, pixels // 4096)].sum().item())
+
+    # ---- (2) end to end through the host-buffer path ----
+    pinned_scans = [torch.empty(s.nbytes, dtype=torch.uint8).pin_memory() for s in sets]
+    for t, s in zip(pinned_scans, sets):
+        t.numpy()[:] = s.view(np.uint8)
+    z_host = torch.empty(pixels, dtype=torch.float32).pin_memory()
+
+    def e2e_step(k):
+        s = pinned_scans[k % n_sets].numpy().view(sets[0].dtype)
+        eng.scan_open(s, z_dev, None, N_NONE, flags, stream)       # H2D of the descriptors inside
+        z_host.copy_(z_dev, non_blocking=True)                      # D2H of the step's result
+        stream.synchronize()
+
+    for k in range(2):
+        e2e_step(k)
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for k in range(args.steps):
+        e2e_step(k)
+    e1.record(stream)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0)) / args.steps
+    e2e_value = world * pixels / (e2e_ms * 1e-3)
+
+    # ---- (3) roofline of the dominant kernel (rank 0) ----
+    out = None
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        fp64_peak = eng.fp64_peak_tflops(8192)
+        fp32_peak = eng.fp32_peak_tflops(8192)
+        k_ms = sum(kernel_ms) / len(kernel_ms)
+        pix_s_kernel = pixels / (k_ms * 1e-3)
+        f_exec, f_ref = flops_factored(N), flops_reference_formulation(N)
+        achieved = pix_s_kernel * f_exec * 1e-12
+        bytes_per_pixel = 4 + N
+        hbm_achieved = pix_s_kernel * bytes_per_pixel * 1e-9
+        roofline = {
+            "bound": "fp64_pipe", "kernel": f"qd_scan_kernel<{N},default>",
+            "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            "peak_kind": "fp64 FMA micro-benchmark run inside this bench (qd_measure_fp64_peak); "
+                         "MEASURED_PEAKS.json has no CUDA-core figure",
+            "flop_per_pixel": f_exec, "flop_per_pixel_reference_formulation": f_ref,
+            "pipe_slot_frac": pix_s_kernel * fp64_pipe_ops_factored(N) * 2e-12 / fp64_peak,
+            "kernel_ms": k_ms, "fp32_peak": fp32_peak,
+            "traffic": None,
+            "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": hbm_achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
+                    "algorithmic_bytes_per_pixel": bytes_per_pixel},
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n_cpu_scans = args.cpu_scans or max(2 * cores, 16)
+            pps, cpix, cdt, kind = cpu_reference_pixels_per_s(mb, sets[0], flags, n_cpu_scans, cores)
+            cpu = {"value": pps, "unit": "pixels/s", "cores": cores, "kind": "port",
+                   "sample": f"{n_cpu_scans} scans ({cpix} pixels) of the same workload, {cdt:.1f} s", "what": kind}
+        out = {
+            "metric": "ground_state_pixels_per_s", "value": value, "unit": "pixels/s",
+            "env_steps_per_s": value / pix_per_env,
+            "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "pixels/s", "env_steps_per_s": e2e_value / pix_per_env,
+                    "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
+                    "h2d_bytes_per_step": int(sets[0].nbytes), "d2h_bytes_per_step": int(pixels * 4)},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum,
+        }
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -132,6 +132,12 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
 int qd_scan_open(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_out, void* n_out, int n_type,
                  unsigned flags, void* stream);
 
+/* The two halves of qd_scan_open, for callers that reuse one set of descriptors (bench.py's HBM-resident timing,
+ * CUDA-graph capture): qd_scan_upload validates and copies the descriptors into the context (stream-ordered);
+ * qd_scan_launch enqueues one launch over the descriptors uploaded last. */
+int qd_scan_upload(qd_ctx* ctx, int n_scan, const qd_scan* scans, void* stream);
+int qd_scan_launch(qd_ctx* ctx, float* z_out, void* n_out, int n_type, unsigned flags, void* stream);
+
 /* Same, with HOST output buffers: runs the launch, copies the results back and synchronises. This is the call the
  * drop-in Python classes make for a single do2d_open. */
 int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_out_host, void* n_out_host,

@@ -35,6 +35,8 @@ struct qd_ctx {
   double* d_pts = nullptr;
   size_t pts_cap = 0;
   cudaEvent_t staged = nullptr;   // h_scans may be rewritten once this has fired
+  int up_n_scan = 0;              // descriptors currently resident in d_scans
+  int up_max_ny = 0;
   int64_t launches = 0;
 };
 
@@ -166,20 +168,31 @@ int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stre
     if (s.ny > mny) mny = s.ny;
   }
   *max_ny = mny;
+  ctx->up_n_scan = n_scan;
+  ctx->up_max_ny = mny;
   const size_t bytes = (size_t)n_scan * sizeof(qd_scan);
   int rc = grow(ctx, &ctx->d_scans, &ctx->scans_cap, bytes);
   if (rc) return rc;
-  QD_CUDA(ctx, cudaEventSynchronize(ctx->staged));   // the previous H2D out of the pinned buffer has finished
-  if (ctx->h_scans_cap < bytes) {
-    if (ctx->h_scans) cudaFreeHost(ctx->h_scans);
-    ctx->h_scans = nullptr;
-    ctx->h_scans_cap = 0;
-    const size_t want = bytes + bytes / 4 + 4096;
-    QD_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scans, want));
-    ctx->h_scans_cap = want;
+  // Descriptors already in pinned host memory (e.g. a torch pin_memory() buffer) are copied straight from there and
+  // must stay untouched until the copy has run; pageable ones go through the context's pinned staging buffer.
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, scans) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();
+  const qd_scan* src = scans;
+  if (!pinned) {
+    QD_CUDA(ctx, cudaEventSynchronize(ctx->staged));   // the previous H2D out of the staging buffer has finished
+    if (ctx->h_scans_cap < bytes) {
+      if (ctx->h_scans) cudaFreeHost(ctx->h_scans);
+      ctx->h_scans = nullptr;
+      ctx->h_scans_cap = 0;
+      const size_t want = bytes + bytes / 4 + 4096;
+      QD_CUDA(ctx, cudaMallocHost((void**)&ctx->h_scans, want));
+      ctx->h_scans_cap = want;
+    }
+    memcpy(ctx->h_scans, scans, bytes);
+    src = ctx->h_scans;
   }
-  memcpy(ctx->h_scans, scans, bytes);
-  QD_CUDA(ctx, cudaMemcpyAsync(ctx->d_scans, ctx->h_scans, bytes, cudaMemcpyHostToDevice, stream));
+  QD_CUDA(ctx, cudaMemcpyAsync(ctx->d_scans, src, bytes, cudaMemcpyHostToDevice, stream));
   QD_CUDA(ctx, cudaEventRecord(ctx->staged, stream));
   return QD_OK;
 }
@@ -316,6 +329,16 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
     for (int j = 0; j < 8; ++j) r[L.o_alpha + j] = p.alpha[j];
     for (int j = 0; j < 8; ++j) r[L.o_pleads + j] = p.p_leads[j];
     for (int j = 0; j < 64; ++j) r[L.o_pinter + j] = p.p_inter[j];
+    for (int j = 0; j < N; ++j) {
+      double sp = 0.0, sn = 0.0;
+      for (int k = 0; k < N; ++k) {
+        if (k == j) continue;
+        const double c = 2.0 * r[L.o_cinv + j * N + k];
+        if (c > 0.0) sp += c; else sn += c;
+      }
+      r[L.o_spos + j] = sp;
+      r[L.o_sneg + j] = sn;
+    }
     if (alg == QD_ALG_TUNNEL && cbg)
       memcpy(r + L.o_cbg, cbg + (size_t)e * (NV - G) * G, sizeof(double) * (NV - G) * G);
   }
@@ -325,6 +348,7 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
   QD_CUDA(ctx, cudaMemcpy(ctx->d_records, host.data(), bytes, cudaMemcpyHostToDevice));
   ctx->L = L;
   ctx->n_env = desc->n_env;
+  ctx->up_n_scan = 0;
   if (alg == QD_ALG_DEFAULT || alg == QD_ALG_THRESHOLDED) {
     const long long total = (long long)desc->n_env << N;
     long long blocks = (total + 255) / 256;
@@ -347,6 +371,23 @@ int qd_scan_open(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_out, vo
   rc = stage_scans(ctx, n_scan, scans, (cudaStream_t)stream, &max_ny);
   if (rc) return rc;
   return launch(ctx, n_scan, ctx->d_scans, max_ny, nullptr, z_out, n_out, n_type, flags, (cudaStream_t)stream);
+}
+
+int qd_scan_upload(qd_ctx* ctx, int n_scan, const qd_scan* scans, void* stream) {
+  if (!ctx) return fail(nullptr, QD_ERR_INVALID, "ctx is NULL");
+  if (!ctx->have_models) return fail(ctx, QD_ERR_STATE, "qd_set_models has not been called");
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int max_ny = 0;
+  return stage_scans(ctx, n_scan, scans, (cudaStream_t)stream, &max_ny);
+}
+
+int qd_scan_launch(qd_ctx* ctx, float* z_out, void* n_out, int n_type, unsigned flags, void* stream) {
+  int rc = validate_launch(ctx, n_type, flags, n_out);
+  if (rc) return rc;
+  if (ctx->up_n_scan <= 0) return fail(ctx, QD_ERR_STATE, "qd_scan_upload has not been called");
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return launch(ctx, ctx->up_n_scan, ctx->d_scans, ctx->up_max_ny, nullptr, z_out, n_out, n_type, flags,
+                (cudaStream_t)stream);
 }
 
 int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_out_host, void* n_out_host, int n_type,

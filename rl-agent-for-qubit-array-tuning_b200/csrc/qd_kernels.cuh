@@ -147,7 +147,8 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
     for (int j = 0; j < N; ++j) s = fma(cinv[i * N + j], r[j], s);
     lin[i] = 2.0 * s;
   }
-  // thresholded: dots that keep only round(n_c).  bit (N-1-j) <-> dot j
+  // Restrictions on the candidate box.  bit (N-1-j) <-> dot j;  fixmask: bit is fixed, fixval: its value.
+  // (1) thresholded: dots that keep only round(n_c).
   unsigned fixmask = 0, fixval = 0;
   if (thresholded) {
     const double half_thr = 0.5 * rec[L.o_par + QD_PAR_THRESHOLD];
@@ -160,6 +161,26 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
       }
     }
   }
+  const unsigned thr_mask = fixmask, thr_val = fixval;
+  // (2) exact dominance: raising dot j from 0 to 1 changes E by  a_j + 2 sum_{k != j} Cinv_jk delta_k, which lies in
+  //     [a_j + sneg_j, a_j + spos_j] whatever the other dots do (a_j = 2 h_j + Cinv_jj).  If that interval is strictly
+  //     positive the minimiser has delta_j = 0, if strictly negative delta_j = 1.  Only the undecided dots are
+  //     enumerated; the 1e-9 guard keeps every near-tie inside the enumeration, so the argmin is unchanged.
+  {
+    const double* __restrict__ spos = rec + L.o_spos;
+    const double* __restrict__ sneg = rec + L.o_sneg;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const unsigned bit = 1u << (N - 1 - j);
+      const double aj = lin[j] + cinv[j * N + j];
+      const bool zero = aj + sneg[j] > 1e-9;
+      const bool one = aj + spos[j] < -1e-9;
+      if (!(fixmask & bit) && (zero || one)) {
+        fixmask |= bit;
+        if (one) fixval |= bit;
+      }
+    }
+  }
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   double llo[LOC];
   llo[0] = 0.0;
@@ -167,30 +188,47 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   for (int p = 0; p < NLO; ++p)
 #pragma unroll
     for (int b = 0; b < (1 << p); ++b) llo[b + (1 << p)] = llo[b] + lin[N - 1 - p];
-  if (thresholded) {
 #pragma unroll
-    for (int b = 0; b < LOC; ++b)
-      if (((unsigned)b ^ fixval) & fixmask & (LOC - 1)) llo[b] = INF;
-  }
+  for (int b = 0; b < LOC; ++b)
+    if (((unsigned)b ^ fixval) & fixmask & (LOC - 1)) llo[b] = INF;
 
-  double best = INF;
-  int bidx = 0;
+  double best = INF, best_m = INF;
+  int best_h = 0;
 #pragma unroll 1
   for (int H = 0; H < (1 << NHI); ++H) {
+    const bool ok = !((((unsigned)H << NLO) ^ fixval) & fixmask & ~(unsigned)(LOC - 1));
+    if (!__any_sync(0xffffffffu, ok)) continue;          // no pixel of this warp still allows these high bits
     double lh = 0.0;
 #pragma unroll
     for (int p = 0; p < NHI; ++p) lh += ((H >> p) & 1) ? lin[N - 1 - NLO - p] : 0.0;
-    if (thresholded && ((((unsigned)H << NLO) ^ fixval) & fixmask & ~(unsigned)(LOC - 1))) lh = INF;
+    if (!ok) lh = INF;
     const double* __restrict__ q = Q + (H << NLO);
-    double m = INF;
+    double m0 = INF, m1 = INF;                            // two independent min chains
+    if constexpr (LOC >= 2) {
+#pragma unroll
+      for (int b = 0; b < LOC; b += 2) {
+        const double2 qq = *reinterpret_cast<const double2*>(q + b);
+        const double e0 = llo[b] + qq.x;
+        const double e1 = llo[b + 1] + qq.y;
+        m0 = (e0 < m0) ? e0 : m0;
+        m1 = (e1 < m1) ? e1 : m1;
+      }
+    } else {
+      m0 = llo[0] + q[0];
+    }
+    const double m = (m1 < m0) ? m1 : m0;
+    const double e = m + lh;
+    if (e < best) { best = e; best_m = m; best_h = H; }
+  }
+  // index of the first candidate of the winning high half that attains the minimum (ascending order, ties -> lowest)
+  int bidx = best_h << NLO;
+  {
+    const double* __restrict__ q = Q + (best_h << NLO);
     int mb = 0;
 #pragma unroll
-    for (int b = 0; b < LOC; ++b) {
-      const double e = llo[b] + q[b];
-      if (e < m) { m = e; mb = b; }
-    }
-    const double e = m + lh;
-    if (e < best) { best = e; bidx = (H << NLO) | mb; }
+    for (int b = LOC - 1; b >= 0; --b)
+      if (llo[b] + q[b] == best_m) mb = b;
+    bidx |= mb;
   }
 
   if (kT > 0.0) {
@@ -200,12 +238,21 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
     double acc[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) acc[j] = 0.0;
+    // every candidate the algorithm allows carries weight: drop the dominance restrictions, keep the thresholded ones
+    llo[0] = 0.0;
+#pragma unroll
+    for (int p = 0; p < NLO; ++p)
+#pragma unroll
+      for (int b = 0; b < (1 << p); ++b) llo[b + (1 << p)] = llo[b] + lin[N - 1 - p];
+#pragma unroll
+    for (int b = 0; b < LOC; ++b)
+      if (((unsigned)b ^ thr_val) & thr_mask & (LOC - 1)) llo[b] = INF;
 #pragma unroll 1
     for (int H = 0; H < (1 << NHI); ++H) {
       double lh = 0.0;
 #pragma unroll
       for (int p = 0; p < NHI; ++p) lh += ((H >> p) & 1) ? lin[N - 1 - NLO - p] : 0.0;
-      if (thresholded && ((((unsigned)H << NLO) ^ fixval) & fixmask & ~(unsigned)(LOC - 1))) continue;
+      if ((((unsigned)H << NLO) ^ thr_val) & thr_mask & ~(unsigned)(LOC - 1)) continue;
       const double* __restrict__ q = Q + (H << NLO);
       double wh = 0.0;
 #pragma unroll
@@ -463,35 +510,41 @@ __global__ void __launch_bounds__(128, 3) qd_scan_kernel(const KArgs a) {
             while (true) {
               const unsigned diff = __ballot_sync(0xffffffffu, key != held_key) & todo;
               if (!diff) break;
-              const int i = __ffs(diff) - 1;
+              const int i = __ffs(diff) - 1;                 // first pixel whose ground state differs from the held one
               const uint64_t ck = shfl_u64(key, i);
-              const float u = __shfl_sync(0xffffffffu, u_latch, i);
               const uint64_t x = ck ^ held_key;
               const uint64_t nz = (((x & 0x7f7f7f7f7f7f7f7fULL) + 0x7f7f7f7f7f7f7f7fULL) | x) & 0x8080808080808080ULL;
               const int ndiff = __popcll(nz);
-              bool accept = true;
+              double p_acc = 2.0;                            // > every uniform: accept
               if (ndiff == 1) {
-                const int d0 = (__ffsll((long long)nz) - 1) >> 3;
-                accept = (double)u < rec[L.o_pleads + d0];
+                p_acc = rec[L.o_pleads + ((__ffsll((long long)nz) - 1) >> 3)];
               } else if (ndiff == 2) {
                 const int d0 = (__ffsll((long long)nz) - 1) >> 3;
                 const int d1 = (63 - __clzll((long long)nz)) >> 3;
-                accept = (double)u < rec[L.o_pinter + d0 * 8 + d1];
+                p_acc = rec[L.o_pinter + d0 * 8 + d1];
               }
-              if (accept) {
-                held_key = ck;
-              } else {
-                // pixel i keeps the configuration of the pixel before it
+              // The pixels from i on that want the same new configuration form a run; every one of them faces the same
+              // (held -> ck) transition, so the first of them whose uniform is below p_acc accepts and the ones before
+              // it stay latched to the held configuration.
+              const unsigned from_i = ~((1u << i) - 1u);
+              const unsigned same = __ballot_sync(0xffffffffu, key == ck) & todo & from_i;
+              const unsigned run = same & ~((~same & from_i & todo) ? (~0u << (__ffs(~same & from_i & todo) - 1)) : 0u);
+              const unsigned acc = __ballot_sync(0xffffffffu, (double)u_latch < p_acc) & run;
+              const int a = acc ? __ffs(acc) - 1 : 32;       // accepting pixel (32: nobody in this run)
+              const unsigned rejected = run & ((a >= 32) ? ~0u : ((1u << a) - 1u));
+              if (rejected) {
                 const int src = (i > 0) ? i - 1 : 0;
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                   const double prev = shfl_f64(nd[j], src);
                   const double held = (i > 0) ? prev : d_carry[j];
-                  if (lane == i) nd[j] = held;
+                  if ((rejected >> lane) & 1u) nd[j] = held;
                 }
-                if (lane == i) key = held_key;
+                if ((rejected >> lane) & 1u) key = held_key;
               }
-              todo &= ~((2u << i) - 1u);
+              if (a < 32) held_key = ck;
+              const int done_to = (a < 32) ? a : (31 - __clz(run));
+              todo &= ~((2u << done_to) - 1u);
             }
             // configuration after the last valid pixel -> carry for the next chunk
             const int last = 31 - __clz(vmask);
@@ -537,12 +590,14 @@ __global__ void __launch_bounds__(128, 3) qd_scan_kernel(const KArgs a) {
           for (int j = 0; j < N; ++j) base = fma(rec[L.o_sw + j], nd[j] - g[j], base);
           base *= 2.0;
           const double t = (rint(us) + noise_in) - us;
+          // dPhi_k = css (2 (t + k) + 1) + base is affine in k: x_k = dPhi_k / gamma = x0 + k * xs
+          const double xs = 2.0 * css * inv_gamma;
+          const double x0 = fma(css, fma(2.0, t, 1.0), base) * inv_gamma;
           float zs = 0.f;
 #pragma unroll
           for (int k = -5; k < 5; ++k) {
-            const double dphi = fma(css, 2.0 * (t + (double)k) + 1.0, base);
-            const float xk = (float)(dphi * inv_gamma);
-            zs += 1.0f / fmaf(xk, xk, 1.0f);
+            const float xk = (float)fma((double)k, xs, x0);
+            zs += __frcp_rn(fmaf(xk, xk, 1.0f));
           }
           double z = (double)zs + noise_out;
           if (f_radial && sc->rad_mode == 1) {

@@ -33,6 +33,8 @@ struct qd_layout {
   int32_t o_alpha;   // [8]        barrier alphas (tunnel)
   int32_t o_pleads;  // [8]
   int32_t o_pinter;  // [64]       stride 8
+  int32_t o_spos;    // [8]        2 * sum_{k != j} max(Cinv_jk, 0)   (dominance bounds of the candidate search)
+  int32_t o_sneg;    // [8]        2 * sum_{k != j} min(Cinv_jk, 0)
   int32_t o_q;       // [2^N]      Q[delta] = delta^T cdd_inv delta, delta in {0,1}^N, dot 0 = most significant bit
   int32_t o_cbg;     // [B*G]      (tunnel)
   int32_t rec_doubles;  // total, multiple of 2 (16 bytes)
@@ -53,6 +55,8 @@ static inline qd_layout qd_make_layout(int n_dot, int n_volt, int n_gate, int al
   L.o_alpha = o;  o += 8;
   L.o_pleads = o; o += 8;
   L.o_pinter = o; o += 64;
+  L.o_spos = o;   o += 8;
+  L.o_sneg = o;   o += 8;
   o = (o + 1) & ~1;                       // Q rows are read as 16-byte pairs
   L.o_q = o;
   if (algorithm == QD_ALG_DEFAULT || algorithm == QD_ALG_THRESHOLDED) o += (1 << n_dot);

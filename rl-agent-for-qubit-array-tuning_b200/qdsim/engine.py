@@ -147,9 +147,20 @@ class Engine:
     def scan_open(self, scans: np.ndarray, z_out, n_out=None, n_type: int = N_NONE, flags: int = 0, stream=None):
         """Asynchronous batched launch into DEVICE buffers (torch tensors or raw pointers)."""
         assert scans.dtype == SCAN_DTYPE and scans.flags.c_contiguous
-        sp = None if stream is None else (stream if isinstance(stream, int) else stream.cuda_stream)
         self._check(self._lib.qd_scan_open(self._ctx, len(scans), _ptr(scans), _ptr(z_out), _ptr(n_out), n_type,
-                                           flags, sp))
+                                           flags, self._stream(stream)))
+
+    @staticmethod
+    def _stream(stream):
+        return None if stream is None else (stream if isinstance(stream, int) else stream.cuda_stream)
+
+    def scan_upload(self, scans: np.ndarray, stream=None):
+        """Copy descriptors to the device once; ``scan_launch`` then re-runs them without any host traffic."""
+        assert scans.dtype == SCAN_DTYPE and scans.flags.c_contiguous
+        self._check(self._lib.qd_scan_upload(self._ctx, len(scans), _ptr(scans), self._stream(stream)))
+
+    def scan_launch(self, z_out, n_out=None, n_type: int = N_NONE, flags: int = 0, stream=None):
+        self._check(self._lib.qd_scan_launch(self._ctx, _ptr(z_out), _ptr(n_out), n_type, flags, self._stream(stream)))
 
     def scan_open_host(self, scans: np.ndarray, n_type: int = N_U8, flags: int = 0, want_z: bool = True):
         """Synchronous launch returning host arrays ``(z float32 [pixels], n [pixels, N] or None)``."""
