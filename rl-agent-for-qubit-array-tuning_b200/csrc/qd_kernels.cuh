@@ -42,76 +42,136 @@ struct KArgs {
 };
 
 constexpr int QD_DER_DOUBLES = 48;  // derived per-item block: g0[8] gx[8] gy[8] us0 usx usy pad[5] carry[8] + spare
+constexpr int QD_PC_DOUBLES = 8 * 64 + 8 * 16 + 8;   // projection cache: 8 matrices, inversion scratch, keys + meta
 
 __host__ __device__ inline int qd_slot_bytes(const qd_layout& L) {
   int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_DER_DOUBLES * 8 + 16;
+  if (L.algorithm == QD_ALG_DEFAULT || L.algorithm == QD_ALG_THRESHOLDED) b += QD_PC_DOUBLES * 8;
   return (b + 127) & ~127;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Exact continuous relaxation: min (n-g)^T cdd^{-1} (n-g), n >= 0  (monotone active set on the M-matrix cdd).
-// oracle/path_a.py: continuous_relaxation.
+// Exact continuous relaxation: min (n-g)^T cdd^{-1} (n-g), n >= 0  (monotone active set on the M-matrix cdd;
+// oracle/path_a.py: continuous_relaxation).
+//
+// For an active (clamped) set S the solution is LINEAR in g:  w = P_S g,  P_S = I - cdd[:,S] (cdd_SS)^{-1} E_S^T, and P_S
+// depends on the env and on S only -- not on the pixel.  A scan meets a handful of distinct S (the swept dots cross
+// zero, the others are clamped or free throughout), so each warp keeps a small cache of P_S matrices in its shared
+// memory slot, built cooperatively by the 32 lanes (Gauss-Jordan on the masked matrix) on a miss.  Per pixel a round
+// of the active-set iteration is then one N x N mat-vec with broadcast shared-memory operands.
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef QD_MIN_BLOCKS
+#define QD_MIN_BLOCKS 3
+#endif
+constexpr int QD_PC_WAYS = 8;
+struct ProjCache {
+  uint32_t* keys;   // [QD_PC_WAYS]
+  uint32_t* meta;   // [0] = entries in use, [1] = next victim
+  double* mats;     // [QD_PC_WAYS][64]
+  double* aug;      // [8][16] scratch of the cooperative inversion
+};
+
 template <int N>
-__device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __restrict__ cdd, double (&nc)[N]) {
+__device__ __noinline__ int proj_cache_build(const ProjCache& pc, const double* __restrict__ cdd, unsigned S, int lane) {
+  constexpr int W = 2 * N;
+  double* A = pc.aug;
+  for (int e = lane; e < N * W; e += 32) {
+    const int r = e / W, c = e - r * W;
+    double v;
+    if (c < N) v = (((S >> r) & 1u) && ((S >> c) & 1u)) ? cdd[r * N + c] : (r == c ? 1.0 : 0.0);
+    else v = (r == c - N) ? 1.0 : 0.0;
+    A[e] = v;
+  }
+  __syncwarp();
+  for (int k = 0; k < N; ++k) {
+    if (!((S >> k) & 1u)) continue;                      // identity pivot
+    const double inv = 1.0 / A[k * W + k];
+    double rowk[(N * W + 31) / 32], fr[(N * W + 31) / 32];
+#pragma unroll
+    for (int t = 0; t < (N * W + 31) / 32; ++t) {
+      const int e = lane + 32 * t;
+      if (e < N * W) {
+        const int r = e / W, c = e - r * W;
+        rowk[t] = A[k * W + c] * inv;
+        fr[t] = A[r * W + k];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < (N * W + 31) / 32; ++t) {
+      const int e = lane + 32 * t;
+      if (e < N * W) {
+        const int r = e / W;
+        A[e] = (r == k) ? rowk[t] : A[e] - fr[t] * rowk[t];
+      }
+    }
+    __syncwarp();
+  }
+  // victim slot (round robin) and P_S = I - cdd[:,S] K[S,:] restricted to columns in S; rows in S are zero
+  const int slot = (int)pc.meta[1];
+  double* P = pc.mats + slot * 64;
+  for (int e = lane; e < N * N; e += 32) {
+    const int i = e / N, j = e - i * N;
+    double v = (i == j) ? 1.0 : 0.0;
+    if ((S >> j) & 1u) {
+      for (int q = 0; q < N; ++q)
+        if ((S >> q) & 1u) v -= cdd[i * N + q] * A[q * W + N + j];
+    }
+    if ((S >> i) & 1u) v = 0.0;
+    P[e] = v;
+  }
+  if (lane == 0) {
+    pc.keys[slot] = S;
+    pc.meta[1] = (uint32_t)((slot + 1) % QD_PC_WAYS);
+    if (pc.meta[0] < QD_PC_WAYS) pc.meta[0] += 1;
+  }
+  __syncwarp();
+  return slot;
+}
+
+template <int N>
+__device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __restrict__ cdd, const ProjCache& pc,
+                                          int lane, double (&nc)[N]) {
   unsigned act = 0;
 #pragma unroll
   for (int j = 0; j < N; ++j) act |= (g[j] < 0.0) ? (1u << j) : 0u;
-  double w[N];
+  bool need = act != 0;
+#pragma unroll
+  for (int j = 0; j < N; ++j) nc[j] = g[j];
 #pragma unroll 1
   for (int round = 0; round <= N; ++round) {
-    double m[N * (N + 1) / 2];
-    double y[N];
+    unsigned pend = __ballot_sync(0xffffffffu, need);
+    if (!pend) break;
+    bool changed = false;
+    while (pend) {
+      const int leader = __ffs(pend) - 1;
+      const unsigned S = __shfl_sync(0xffffffffu, act, leader);
+      const bool member = need && act == S;
+      pend &= ~__ballot_sync(0xffffffffu, member);
+      const unsigned hit = __ballot_sync(0xffffffffu, lane < (int)pc.meta[0] && pc.keys[lane & (QD_PC_WAYS - 1)] == S &&
+                                                          lane < QD_PC_WAYS);
+      const int slot = hit ? __ffs(hit) - 1 : proj_cache_build<N>(pc, cdd, S, lane);
+      if (member) {
+        const double* __restrict__ P = pc.mats + slot * 64;
+        unsigned neu = act;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const bool ai = (act >> i) & 1u;
-      y[i] = ai ? -g[i] : 0.0;
+        for (int i = 0; i < N; ++i) {
+          double sacc = 0.0;
 #pragma unroll
-      for (int j = 0; j <= i; ++j) {
-        const bool both = ai && ((act >> j) & 1u);
-        m[i * (i + 1) / 2 + j] = both ? cdd[i * N + j] : (i == j ? 1.0 : 0.0);
+          for (int j = 0; j < N; ++j) sacc = fma(P[i * N + j], g[j], sacc);
+          sacc = ((act >> i) & 1u) ? 0.0 : sacc;
+          nc[i] = sacc;
+          neu |= (sacc < 0.0) ? (1u << i) : 0u;
+        }
+        changed = neu != act;
+        act = neu;
       }
+      __syncwarp();
     }
-    // LDL^T in place (SPD, no pivoting); forward substitution fused
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const double inv = 1.0 / m[k * (k + 1) / 2 + k];
-      m[k * (k + 1) / 2 + k] = inv;
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) {
-        const double u = m[i * (i + 1) / 2 + k];
-        const double l = u * inv;
-#pragma unroll
-        for (int j = k + 1; j < i; ++j) m[i * (i + 1) / 2 + j] -= u * m[j * (j + 1) / 2 + k];
-        m[i * (i + 1) / 2 + i] -= u * l;
-        y[i] -= l * y[k];
-        m[i * (i + 1) / 2 + k] = l;
-      }
-    }
-    double mu[N];
-#pragma unroll
-    for (int k = N - 1; k >= 0; --k) {
-      double s = y[k] * m[k * (k + 1) / 2 + k];
-#pragma unroll
-      for (int i = k + 1; i < N; ++i) s -= m[i * (i + 1) / 2 + k] * mu[i];
-      mu[k] = s;
-    }
-    unsigned neu = act;
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double s = g[i];
-#pragma unroll
-      for (int j = 0; j < N; ++j) s = fma(cdd[i * N + j], mu[j], s);
-      s = ((act >> i) & 1u) ? 0.0 : s;
-      w[i] = s;
-      neu |= (s < 0.0) ? (1u << i) : 0u;
-    }
-    const bool changed = neu != act;
-    act = neu;
-    if (!__any_sync(0xffffffffu, changed)) break;
+    need = changed;
   }
 #pragma unroll
-  for (int j = 0; j < N; ++j) nc[j] = fmax(w[j], 0.0);
+  for (int j = 0; j < N; ++j) nc[j] = fmax(nc[j], 0.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -119,7 +179,8 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
 // ---------------------------------------------------------------------------------------------------------------
 template <int N>
 __device__ __forceinline__ void ground_state_box(const double (&g)[N], const double* __restrict__ rec,
-                                                 const qd_layout& L, bool thresholded, double kT, double (&nd)[N]) {
+                                                 const qd_layout& L, const ProjCache& pc, int lane, bool thresholded,
+                                                 double kT, double (&nd)[N]) {
   constexpr int NLO = N < 4 ? N : 4;
   constexpr int NHI = N - NLO;
   constexpr int LOC = 1 << NLO;
@@ -132,7 +193,7 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   double nc[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) nc[j] = g[j];
-  if (__any_sync(0xffffffffu, neg)) relax_lcp<N>(g, rec + L.o_cdd, nc);
+  if (__any_sync(0xffffffffu, neg)) relax_lcp<N>(g, rec + L.o_cdd, pc, lane, nc);
 
   double f[N], r[N], lin[N];
 #pragma unroll
@@ -366,7 +427,7 @@ __device__ __forceinline__ uint64_t pack_key(const double (&nd)[N]) {
 }
 
 template <int N, int ALG>
-__global__ void __launch_bounds__(128, 3) qd_scan_kernel(const KArgs a) {
+__global__ void __launch_bounds__(128, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs a) {
   extern __shared__ __align__(128) unsigned char qd_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -384,6 +445,11 @@ __global__ void __launch_bounds__(128, 3) qd_scan_kernel(const KArgs a) {
   double* d_gy = der + 16;
   double* d_us = der + 24;      // us0, usx, usy
   double* d_carry = der + 32;   // latched configuration of the last pixel of the previous chunk
+  ProjCache pc;
+  pc.mats = reinterpret_cast<double*>(bar + 2);
+  pc.aug = pc.mats + 8 * 64;
+  pc.keys = reinterpret_cast<uint32_t*>(pc.aug + 8 * 16);
+  pc.meta = pc.keys + QD_PC_WAYS;
 
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
@@ -414,6 +480,9 @@ __global__ void __launch_bounds__(128, 3) qd_scan_kernel(const KArgs a) {
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
+    if constexpr (ALG != QD_ALG_BRUTE_FORCE) {
+      if (lane == 0) { pc.meta[0] = 0u; pc.meta[1] = 0u; }    // the projection cache belongs to one env
+    }
 
     const int nx = sc->nx, ny = sc->ny;
     const int row0 = part * a.rows_per_item;
@@ -496,7 +565,7 @@ __global__ void __launch_bounds__(128, 3) qd_scan_kernel(const KArgs a) {
 
           // ---- ground state ----
           if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N>(g, rec, L, kT, nd);
-          else ground_state_box<N>(g, rec, L, L.algorithm == QD_ALG_THRESHOLDED, kT, nd);
+          else ground_state_box<N>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, nd);
 
           // ---- hysteresis latching along x ----
           if (latch_on) {
