@@ -149,6 +149,9 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   const size_t smem = (size_t)a.slot_bytes * wpc;
   if (smem > 48 * 1024)
     QD_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // every warp stages its own record: ask for the largest shared-memory carveout so that registers, not shared
+  // memory, bound the resident warps
+  QD_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   fn<<<(unsigned)grid, wpc * 32, smem, stream>>>(a);
   QD_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;

@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 // order prior generic-proxy accesses to shared memory before subsequent async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// MUFU.RCP, ~1 ulp: the Lorentzian sum tolerates it (error budget of the sensor signal)
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double shfl_f64(double v, int src) {
   int lo = __double2loint(v), hi = __double2hiint(v);

@@ -255,10 +255,22 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
 
   double best = INF, best_m = INF;
   int best_h = 0;
+  // high halves H still allowed for this pixel, as a bit set over H; one warp-wide OR gives the H values the warp has
+  // to visit at all (a single REDUX instead of a vote per H)
+  unsigned okset = (NHI == 0) ? 1u : ((NHI >= 5) ? 0xffffffffu : ((1u << (1 << NHI)) - 1u));
+#pragma unroll
+  for (int p = 0; p < NHI; ++p) {
+    // H values whose bit p is set: 0xAAAAAAAA, 0xCCCCCCCC, 0xF0F0F0F0, 0xFF00FF00, 0xFFFF0000
+    const unsigned ones = (p == 0) ? 0xAAAAAAAAu : (p == 1) ? 0xCCCCCCCCu : (p == 2) ? 0xF0F0F0F0u : (p == 3) ? 0xFF00FF00u : 0xFFFF0000u;
+    const unsigned bit = 1u << (NLO + p);
+    if (fixmask & bit) okset &= (fixval & bit) ? ones : ~ones;
+  }
+  unsigned visit = __reduce_or_sync(0xffffffffu, okset);
 #pragma unroll 1
-  for (int H = 0; H < (1 << NHI); ++H) {
-    const bool ok = !((((unsigned)H << NLO) ^ fixval) & fixmask & ~(unsigned)(LOC - 1));
-    if (!__any_sync(0xffffffffu, ok)) continue;          // no pixel of this warp still allows these high bits
+  while (visit) {
+    const int H = __ffs(visit) - 1;
+    visit &= visit - 1u;
+    const bool ok = (okset >> H) & 1u;
     double lh = 0.0;
 #pragma unroll
     for (int p = 0; p < NHI; ++p) lh += ((H >> p) & 1) ? lin[N - 1 - NLO - p] : 0.0;
@@ -666,15 +678,16 @@ __global__ void __launch_bounds__(128, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs
 #pragma unroll
           for (int k = -5; k < 5; ++k) {
             const float xk = (float)fma((double)k, xs, x0);
-            zs += __frcp_rn(fmaf(xk, xk, 1.0f));
+            zs += rcp_approx(fmaf(xk, xk, 1.0f));
           }
           double z = (double)zs + noise_out;
           if (f_radial && sc->rad_mode == 1) {
-            const double vx = fma((double)ixc, sc->rad_dx, sc->rad_x0);
-            const double vy = fma((double)iy, sc->rad_dy, sc->rad_y0);
-            const double dist = sqrt(vx * vx + vy * vy);
-            const double amp = fmin(fmax(sc->rad_alpha * (dist - sc->rad_zero_radius), 0.0), sc->rad_max_amp);
-            z = fma((double)z_rad, amp, z);
+            const float vx = (float)fma((double)ixc, sc->rad_dx, sc->rad_x0);
+            const float vy = (float)fma((double)iy, sc->rad_dy, sc->rad_y0);
+            const float dist = sqrtf(fmaf(vx, vx, vy * vy));
+            const float amp = fminf(fmaxf((float)sc->rad_alpha * (dist - (float)sc->rad_zero_radius), 0.0f),
+                                    (float)sc->rad_max_amp);
+            z = fma((double)z_rad, (double)amp, z);
           }
           zf = (float)z;
         } else {

@@ -1,0 +1,46 @@
+"""Golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the CPU oracle).
+
+CPU: the oracle and its C port reproduce the committed fixtures.  GPU: the CUDA path reproduces them through the C ABI.
+"""
+import numpy as np
+import pytest
+
+from util import GOLDEN_CASES, compare_charges, load_golden, oracle_batch
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_reproduces_golden(name):
+    mb, scans, flags, z, n, margin = load_golden(name)
+    z2, n2, m2 = oracle_batch(mb, scans, flags)
+    assert np.array_equal(n2, n)
+    np.testing.assert_allclose(z2, z, rtol=1e-12, atol=1e-14)
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cport_reproduces_golden(name):
+    from oracle import cport
+    from qdsim import FLAG_THERMAL
+    mb, scans, flags, z, n, margin = load_golden(name)
+    zc, nc, _ = cport.run_scans(mb, scans, flags, threads=2)
+    if flags & FLAG_THERMAL:
+        np.testing.assert_allclose(nc.reshape(n.shape), n, rtol=0, atol=1e-10)
+    else:
+        assert np.array_equal(nc.reshape(n.shape), n)
+    np.testing.assert_allclose(zc.reshape(z.shape), z, rtol=3e-7, atol=1e-7)      # C port stores fp32 images
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_gpu_reproduces_golden(engine, name):
+    from qdsim import FLAG_NOISE, FLAG_RADIAL, FLAG_THERMAL, N_F64, N_U8
+    mb, scans, flags, z, n, margin = load_golden(name)
+    engine.set_models(mb)
+    thermal = bool(flags & FLAG_THERMAL)
+    zg, ng = engine.scan_open_host(scans, n_type=N_F64 if thermal else N_U8, flags=flags)
+    zg, ng = zg.reshape(z.shape), ng.reshape(n.shape)
+    if thermal:
+        np.testing.assert_allclose(ng, n, rtol=0, atol=1e-9)
+    else:
+        compare_charges(ng, n, margin)
+    noisy = bool(flags & (FLAG_NOISE | FLAG_RADIAL))
+    np.testing.assert_allclose(zg, z, rtol=0 if noisy else 1e-6, atol=5e-6 if noisy else 1e-7 if thermal else 0)

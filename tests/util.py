@@ -64,3 +64,21 @@ def compare_charges(n_gpu, n_ref, margin, tie_tol=1e-9, max_tie_frac=0.005):
     bad = (n_gpu != n_ref).any(axis=-1) & safe
     assert not bad.any(), f"{bad.sum()} of {bad.size} pixels differ, first at {np.argwhere(bad)[:5]}"
     return int((~safe).sum())
+
+
+def load_golden(name):
+    """tests/golden/<name>.npz -> (ModelBatch, scans, flags, z, n, margin): inputs rebuilt through the product's host code
+    from the RAW capacitances stored in the fixture."""
+    import os
+    from qdsim import PARAMS_DTYPE, SCAN_DTYPE
+    from qdsim.engine import ModelBatch
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
+    d = np.load(path)
+    mb = ModelBatch.from_capacitances(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"], algorithm=str(d["algorithm"]))
+    mb.params = d["params"].view(PARAMS_DTYPE).copy()
+    scans = d["scans"].view(SCAN_DTYPE).copy()
+    return mb, scans, int(d["flags"]), d["z"], d["n"], d["margin"]
+
+
+GOLDEN_CASES = ["c1_2dot_64x64_noise_free", "c2_4dot_latched_full_noise", "c2b_4dot_flat_pass", "c3_6dot_brute_force",
+                "c4_8dot_latched_full_noise", "t_3dot_thermal", "t_5dot_thresholded"]
