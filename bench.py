@@ -128,15 +128,25 @@ def _cpu_worker(job):
     return int(rec["nx"][0]) * int(rec["ny"][0]) * len(rec)
 
 
-def cpu_reference_pixels_per_s(mb, scans, flags, n_sample_scans: int, cores: int):
-    """Pixels/s of the CPU restatement over ``n_sample_scans`` scans of the workload using ``cores`` processes."""
+def cpu_reference_pixels_per_s(mb, scans, flags, n_sample_scans: int, cores: int, budget_s: float = 10.0):
+    """Pixels/s of the CPU restatement (reference formulation) over a bounded sample of ``scans`` on ``cores`` threads.
+
+    Preferred: the plain-C restatement with OpenMP (oracle/cport).  ``n_sample_scans == 0`` sizes the sample for about
+    ``budget_s`` seconds from a short calibration run.  Fallback if gcc is missing: the NumPy oracle, one process/core.
+    """
     import multiprocessing as mp
     try:
         from oracle import cport
         if cport.available():
-            return cport.time_scans(mb, scans[:n_sample_scans], flags, threads=cores) + ("port (C restatement, OpenMP)",)
+            cal = min(len(scans), 4 * cores)
+            cport.time_scans(mb, scans[:cal], flags, threads=cores)              # spin the thread pool up
+            rate, cpix, cdt = cport.time_scans(mb, scans[:cal], flags, threads=cores)
+            n = n_sample_scans or int(min(len(scans), max(cal, budget_s * rate / (cpix / cal))))
+            pps, pixels, dt = cport.time_scans(mb, scans[:n], flags, threads=cores)
+            return pps, pixels, dt, "port: plain-C restatement of the reference formulation, OpenMP over scans"
     except ImportError:
         pass
+    n_sample_scans = n_sample_scans or max(2 * cores, 16)
     sample = scans[:n_sample_scans]
     envs = np.unique(sample["env_id"])
     remap = {int(e): i for i, e in enumerate(envs)}
@@ -150,7 +160,7 @@ def cpu_reference_pixels_per_s(mb, scans, flags, n_sample_scans: int, cores: int
     with ctx.Pool(cores) as pool:
         pixels = sum(pool.map(_cpu_worker, jobs, chunksize=1))
     dt = time.perf_counter() - t0
-    return pixels / dt, pixels, dt, "port (NumPy restatement, one process per core)"
+    return pixels / dt, pixels, dt, "port: NumPy restatement, one process per core"
 
 
 def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int):
@@ -193,9 +203,11 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        n_scans = args.cpu_scans or max(cores, 16)
-        n_env_s = max(1, (n_scans + N - 2) // (N - 1))
-        dev, mb, sets = build_workload(n_env_s, N, res, 0, 1)
+        dev, mb, sets = build_workload(min(args.n_env, 512), N, res, 0, 1)
+        n_scans = args.cpu_scans
+        if not n_scans:                       # ~3 s of CPU work per step
+            _, cpix, cdt, _ = cpu_reference_pixels_per_s(mb, sets[0], flags, 4 * cores, cores)
+            n_scans = int(min(len(sets[0]), max(4 * cores, 3.0 * (cpix / cdt) / (res * res))))
         per_step = []
         kind = ""
         for _ in range(args.warmup + args.steps):
@@ -324,10 +336,10 @@ def main():
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            n_cpu_scans = args.cpu_scans or max(2 * cores, 16)
-            pps, cpix, cdt, kind = cpu_reference_pixels_per_s(mb, sets[0], flags, n_cpu_scans, cores)
+            pps, cpix, cdt, kind = cpu_reference_pixels_per_s(mb, sets[0], flags, args.cpu_scans, cores)
             cpu = {"value": pps, "unit": "pixels/s", "cores": cores, "kind": "port",
-                   "sample": f"{n_cpu_scans} scans ({cpix} pixels) of the same workload, {cdt:.1f} s", "what": kind}
+                   "sample": f"{cpix // (res * res)} scans ({cpix} pixels) of the same workload, {cdt:.1f} s",
+                   "what": kind}
         out = {
             "metric": "ground_state_pixels_per_s", "value": value, "unit": "pixels/s",
             "env_steps_per_s": value / pix_per_env,

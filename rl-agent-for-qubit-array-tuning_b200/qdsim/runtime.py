@@ -1,0 +1,44 @@
+"""Process-wide engines for the single-device drop-in classes: one ``Engine`` (qd_ctx) per CUDA device, shared by every
+``ChargeSensedDotArray`` / ``TunnelCoupledChargeSensed`` of the process.  The model object that used an engine last is
+its "owner"; another object re-uploads its own constants first (a few KB)."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from .engine import Engine
+
+_engines: dict[int, Engine] = {}
+_owner: dict[int, int] = {}
+
+
+def default_device() -> int:
+    return int(os.environ.get("QDSIM_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+def engine_for(model, device: int | None = None) -> Engine:
+    """Engine of ``device`` with ``model``'s constants resident (``model._model_batch()`` builds them)."""
+    dev = default_device() if device is None else device
+    eng = _engines.get(dev)
+    if eng is None:
+        eng = _engines[dev] = Engine(dev)
+    key = (id(model), model._version)
+    if _owner.get(dev) != key:
+        eng.set_models(model._model_batch())
+        _owner[dev] = key
+    return eng
+
+
+def fresh_seed() -> int:
+    """A 64-bit scan seed drawn from the process-global ``np.random`` state -- the stream the reference's noise and
+    latching classes consume -- so ``np.random.seed(...)`` makes a run reproducible."""
+    hi, lo = np.random.randint(0, 2 ** 32, size=2, dtype=np.uint64)
+    return int((hi << np.uint64(32)) | lo)
+
+
+def shutdown():
+    for eng in _engines.values():
+        eng.close()
+    _engines.clear()
+    _owner.clear()
