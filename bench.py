@@ -351,6 +351,15 @@ def main():
                     "h2d_bytes_per_step": int(sets[0].nbytes), "d2h_bytes_per_step": int(pixels * 4)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum,
         }
+    # the one collective of the design, OFF the step path: per-env episode statistics to every rank (NCCL all-gather)
+    if world > 1:
+        from qdsim import parallel
+        stats = torch.stack([z_dev.view(args.n_env, -1).mean(dim=1),
+                             torch.full((args.n_env,), float(rank), device="cuda")], dim=1)
+        full = parallel.gather_episode_stats(stats, args.n_env * world)
+        assert full.shape == (args.n_env * world, 2)
+        if rank == 0:
+            out["episode_stats_allgather"] = {"shape": list(full.shape), "ranks_seen": int(full[:, 1].unique().numel())}
     barrier()
     if world > 1:
         dist.destroy_process_group()

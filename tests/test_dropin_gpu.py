@@ -88,7 +88,7 @@ def test_noise_and_latching_models_are_honoured_and_seedable():
     assert np.array_equal(z1, z2) and np.array_equal(n1, n2)
     assert not np.array_equal(z1, z3)
     assert (n1 != n0).any(), "latching with p = 0.3 must delay some transitions"
-    assert 1e-3 < np.abs(z1 - z0)[n1.sum(-1) == n0.sum(-1)].std() < 1.0
+    assert 1e-5 < np.abs(z1 - z0)[n1.sum(-1) == n0.sum(-1)].std() < 1.0
     thermal = _model()
     thermal.T = 100.0
     nt = thermal.ground_state_open(np.array([[-0.52, -0.5, 0.0]]))

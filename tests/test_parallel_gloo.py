@@ -1,0 +1,61 @@
+"""The N>1 host logic on CPU: env sharding and the episode-stat all-gather, world_size 2 and 3 over gloo."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n_env, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "rl-agent-for-qubit-array-tuning_b200"))
+    from qdsim import parallel, synth
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = parallel.shard_range(n_env, rank, world)
+    # every rank builds only its own shard of devices and scan descriptors (what bench.py does per rank)
+    dev = synth.sample_devices(hi - lo, 3, seed=100 + rank)
+    mb = synth.model_batch(dev)
+    scans = synth.env_step_scans(mb, dev, res=8, seed=1)
+    assert len(scans) == (hi - lo) * 2 and scans["env_id"].max() == hi - lo - 1
+    stats = torch.stack([torch.arange(lo, hi, dtype=torch.float32), torch.full((hi - lo,), float(rank))], dim=1)
+    full = parallel.gather_episode_stats(stats, n_env)
+    ok = full.shape == (n_env, 2) and torch.equal(full[:, 0], torch.arange(n_env, dtype=torch.float32))
+    owners = [r for r in range(world) for _ in range(*parallel.shard_range(n_env, r, world))]
+    ok = ok and torch.equal(full[:, 1], torch.tensor(owners, dtype=torch.float32))
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_env", [(2, 10), (3, 10), (2, 7)])
+def test_sharding_and_stat_gather_over_gloo(world, n_env):
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, n_env, out), nprocs=world, join=True)
+        assert all(out[r] for r in range(world)) and len(out) == world
+
+
+def test_shard_ranges_partition_the_envs():
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "rl-agent-for-qubit-array-tuning_b200"))
+    from qdsim import parallel
+    for n_env in (1, 7, 16384, 16385):
+        for world in (1, 2, 3, 8):
+            ranges = [parallel.shard_range(n_env, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n_env
+            assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_range(4, 4, 4)
