@@ -64,6 +64,33 @@ __host__ __device__ inline int qd_slot_bytes(const qd_layout& L) {
 #define QD_MIN_BLOCKS 3
 #endif
 constexpr int QD_PC_WAYS = 8;
+
+// y = M x for a row-major N x N fp64 matrix in shared memory (16-byte aligned), all lanes reading the same elements:
+// broadcast LDS.128 fetches two matrix entries per load when N is even.
+template <int N>
+__device__ __forceinline__ void matvec_smem(const double* __restrict__ M, const double (&x)[N], double (&y)[N]) {
+  if constexpr (N % 2 == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        const double2 m = *reinterpret_cast<const double2*>(M + i * N + j);
+        s0 = fma(m.x, x[j], s0);
+        s1 = fma(m.y, x[j + 1], s1);
+      }
+      y[i] = s0 + s1;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      double s0 = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) s0 = fma(M[i * N + j], x[j], s0);
+      y[i] = s0;
+    }
+  }
+}
 struct ProjCache {
   uint32_t* keys;   // [QD_PC_WAYS]
   uint32_t* meta;   // [0] = entries in use, [1] = next victim
@@ -154,12 +181,11 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
       if (member) {
         const double* __restrict__ P = pc.mats + slot * 64;
         unsigned neu = act;
+        double wv[N];
+        matvec_smem<N>(P, g, wv);
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-          double sacc = 0.0;
-#pragma unroll
-          for (int j = 0; j < N; ++j) sacc = fma(P[i * N + j], g[j], sacc);
-          sacc = ((act >> i) & 1u) ? 0.0 : sacc;
+          const double sacc = ((act >> i) & 1u) ? 0.0 : wv[i];
           nc[i] = sacc;
           neu |= (sacc < 0.0) ? (1u << i) : 0u;
         }
@@ -201,13 +227,9 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
     f[j] = floor(nc[j]);
     r[j] = f[j] - g[j];
   }
+  matvec_smem<N>(cinv, r, lin);
 #pragma unroll
-  for (int i = 0; i < N; ++i) {
-    double s = 0.0;
-#pragma unroll
-    for (int j = 0; j < N; ++j) s = fma(cinv[i * N + j], r[j], s);
-    lin[i] = 2.0 * s;
-  }
+  for (int i = 0; i < N; ++i) lin[i] *= 2.0;
   // Restrictions on the candidate box.  bit (N-1-j) <-> dot j;  fixmask: bit is fixed, fixval: its value.
   // (1) thresholded: dots that keep only round(n_c).
   unsigned fixmask = 0, fixval = 0;
