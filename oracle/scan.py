@@ -63,8 +63,7 @@ def simulate_scan(m: Model, s: Scan, latch_compare: str = "rounded", carry_rows:
     v = composer.affine_grid(s.v0, s.dx, s.dy, nx, ny).reshape(ny * nx, -1)
     if m.algorithm == "tunnel":
         from . import path_b
-        n = path_b.ground_state_open(m, v)
-        margin = np.full(ny * nx, np.inf)
+        n, margin = path_b.ground_state_open(m, v, return_gap=True)     # "margin" = spectral gap of the pixel
     else:
         n, margin = path_a.ground_state_open(v, m.cgd, m.cdd_inv, m.cdd, m.algorithm, m.threshold,
                                              m.max_charge_carriers, m.kT, return_margin=True)

@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "qd_kernels.cuh"
+#include "qd_tunnel.cuh"
 
 static_assert(sizeof(qd_scan) == 480, "qd_scan must be 480 bytes (multiple of 16 for the TMA bulk copy)");
 static_assert(sizeof(qd_scan) % 16 == 0, "qd_scan size");
@@ -34,9 +35,13 @@ struct qd_ctx {
   size_t n_cap = 0;
   double* d_pts = nullptr;
   size_t pts_cap = 0;
+  double* d_nbar = nullptr;       // tunnel path: <n> of every pixel between the two launches
+  size_t nbar_cap = 0;
   cudaEvent_t staged = nullptr;   // h_scans may be rewritten once this has fired
   int up_n_scan = 0;              // descriptors currently resident in d_scans
   int up_max_ny = 0;
+  long long up_pixels = 0;        // extent of the output buffers they address
+  long long up_max_pix = 0;       // largest scan, in pixels
   int64_t launches = 0;
 };
 
@@ -98,10 +103,63 @@ kernel_fn pick_n(int n) {
   }
 }
 
+kernel_fn pick_tunnel_gs(int n) {
+  switch (n) {
+    case 2: return qd::qd_tunnel_gs_kernel<2>;
+    case 3: return qd::qd_tunnel_gs_kernel<3>;
+    case 4: return qd::qd_tunnel_gs_kernel<4>;
+    case 5: return qd::qd_tunnel_gs_kernel<5>;
+    case 6: return qd::qd_tunnel_gs_kernel<6>;
+    case 7: return qd::qd_tunnel_gs_kernel<7>;
+    case 8: return qd::qd_tunnel_gs_kernel<8>;
+    default: return nullptr;
+  }
+}
+
 kernel_fn pick_kernel(const qd_layout& L) {
+  if (L.algorithm == QD_ALG_TUNNEL) return pick_n<QD_ALG_TUNNEL>(L.n_dot);
   if (L.algorithm == QD_ALG_BRUTE_FORCE) return pick_n<QD_ALG_BRUTE_FORCE>(L.n_dot);
   if (L.algorithm == QD_ALG_DEFAULT || L.algorithm == QD_ALG_THRESHOLDED) return pick_n<QD_ALG_DEFAULT>(L.n_dot);
   return nullptr;
+}
+
+// Tunnel path: Schur complement of the high block and the quadratic tables of the two halves of the candidate digits.
+bool pack_tunnel_tables(const qd_layout& L, double* r) {
+  const int N = L.n_dot, nlo = N < 4 ? N : 4, nhi = N - nlo;
+  const double* C = r + L.o_cinv;
+  // Cll^-1 by Gauss-Jordan (SPD, tiny)
+  double a[4][8];
+  for (int i = 0; i < nlo; ++i)
+    for (int j = 0; j < nlo; ++j) { a[i][j] = C[(nhi + i) * N + nhi + j]; a[i][nlo + j] = (i == j) ? 1.0 : 0.0; }
+  for (int k = 0; k < nlo; ++k) {
+    const double piv = a[k][k];
+    if (!(piv > 0.0)) return false;
+    for (int j = 0; j < 2 * nlo; ++j) a[k][j] /= piv;
+    for (int i = 0; i < nlo; ++i) {
+      if (i == k) continue;
+      const double f = a[i][k];
+      for (int j = 0; j < 2 * nlo; ++j) a[i][j] -= f * a[k][j];
+    }
+  }
+  for (int i = 0; i < nhi; ++i)
+    for (int j = 0; j < nhi; ++j) {
+      double s = C[i * N + j];
+      for (int p = 0; p < nlo; ++p)
+        for (int q = 0; q < nlo; ++q) s -= C[i * N + nhi + p] * a[p][nlo + q] * C[(nhi + q) * N + j];
+      r[L.o_schur + i * nhi + j] = s;
+    }
+  for (int half = 0; half < 2; ++half) {
+    const int nd = half ? nlo : nhi, off = half ? nhi : 0, base = half ? L.o_qll : L.o_qhh;
+    for (int idx = 0; idx < (1 << (2 * nd)); ++idx) {
+      double x[4];
+      for (int j = 0; j < nd; ++j) x[j] = (double)((idx >> (2 * (nd - 1 - j))) & 3) - 1.0;
+      double s = 0.0;
+      for (int i = 0; i < nd; ++i)
+        for (int j = 0; j < nd; ++j) s += x[i] * C[(off + i) * N + off + j] * x[j];
+      r[base + idx] = s;
+    }
+  }
+  return true;
 }
 
 int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) {
@@ -122,6 +180,37 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   kernel_fn fn = pick_kernel(ctx->L);
   if (!fn) return fail(ctx, QD_ERR_UNSUPPORTED, "no kernel for n_dot=%d algorithm=%d", ctx->L.n_dot, ctx->L.algorithm);
   qd::KArgs a;
+  a.nbar = nullptr;
+  if (ctx->L.algorithm == QD_ALG_TUNNEL) {
+    // launch 1 of 2: tunnel-coupled ground state, one warp per pixel, every pixel of every scan independent
+    kernel_fn gs = pick_tunnel_gs(ctx->L.n_dot);
+    if (!gs) return fail(ctx, QD_ERR_UNSUPPORTED, "tunnel path needs 2..8 dots, got %d", ctx->L.n_dot);
+    int rc = grow(ctx, &ctx->d_nbar, &ctx->nbar_cap, (size_t)ctx->up_pixels * ctx->L.n_dot * sizeof(double));
+    if (rc) return rc;
+    qd::KArgs g;
+    g.L = ctx->L; g.records = ctx->d_records; g.scans = d_scans; g.points = d_points; g.z_out = nullptr;
+    g.n_out = nullptr; g.nbar = ctx->d_nbar; g.n_scan = n_scan; g.n_type = QD_N_NONE; g.flags = flags;
+    g.slot_bytes = qd::qd_tunnel_slot_bytes(ctx->L);
+    const long long max_pix = ctx->up_max_pix;
+    const long long want_items = (long long)ctx->sm_count * 8 * 4;
+    long long ppi = ((long long)n_scan * max_pix) / want_items;          // pixels per item
+    if (ppi < 1) ppi = 1;
+    if (ppi > 64) ppi = 64;
+    g.rows_per_item = (int)ppi;
+    g.items_per_scan = (int)((max_pix + ppi - 1) / ppi);
+    const long long items = (long long)n_scan * g.items_per_scan;
+    const int gw = (items < (long long)ctx->sm_count * 4) ? 1 : 4;
+    long long ggrid = (items + gw - 1) / gw;
+    if (ggrid > 0x7fffffffLL) ggrid = 0x7fffffffLL;
+    const size_t gsmem = (size_t)g.slot_bytes * gw;
+    if (gsmem > 48 * 1024)
+      QD_CUDA(ctx, cudaFuncSetAttribute((const void*)gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+    QD_CUDA(ctx, cudaFuncSetAttribute((const void*)gs, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    gs<<<(unsigned)ggrid, gw * 32, gsmem, stream>>>(g);
+    QD_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    a.nbar = ctx->d_nbar;
+  }
   a.L = ctx->L;
   a.records = ctx->d_records;
   a.scans = d_scans;
@@ -162,8 +251,12 @@ int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stre
   if (n_scan <= 0) return fail(ctx, QD_ERR_INVALID, "n_scan must be positive");
   if (!scans) return fail(ctx, QD_ERR_INVALID, "scans is NULL");
   int mny = 0;
+  long long ext = 0, mpix = 0;
   for (int i = 0; i < n_scan; ++i) {
     const qd_scan& s = scans[i];
+    const long long np_ = (long long)s.nx * s.ny;
+    if (s.pix_offset + np_ > ext) ext = s.pix_offset + np_;
+    if (np_ > mpix) mpix = np_;
     if (s.env_id < 0 || s.env_id >= ctx->n_env)
       return fail(ctx, QD_ERR_INVALID, "scan %d: env_id %d out of range [0,%d)", i, s.env_id, ctx->n_env);
     if (s.nx <= 0 || s.ny <= 0) return fail(ctx, QD_ERR_INVALID, "scan %d: nx, ny must be positive", i);
@@ -173,6 +266,8 @@ int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stre
   *max_ny = mny;
   ctx->up_n_scan = n_scan;
   ctx->up_max_ny = mny;
+  ctx->up_pixels = ext;
+  ctx->up_max_pix = mpix;
   const size_t bytes = (size_t)n_scan * sizeof(qd_scan);
   int rc = grow(ctx, &ctx->d_scans, &ctx->scans_cap, bytes);
   if (rc) return rc;
@@ -269,6 +364,7 @@ void qd_destroy(qd_ctx* ctx) {
   if (ctx->d_z) cudaFree(ctx->d_z);
   if (ctx->d_n) cudaFree(ctx->d_n);
   if (ctx->d_pts) cudaFree(ctx->d_pts);
+  if (ctx->d_nbar) cudaFree(ctx->d_nbar);
   if (ctx->staged) cudaEventDestroy(ctx->staged);
   delete ctx;
 }
@@ -290,7 +386,15 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
     return fail(ctx, QD_ERR_INVALID, "bad n_volt=%d / n_gate=%d (max %d)", NV, G, QD_MAX_VOLT);
   const int alg = desc->algorithm;
   if (alg < QD_ALG_DEFAULT || alg > QD_ALG_TUNNEL) return fail(ctx, QD_ERR_INVALID, "Algorithm %d not supported", alg);
-  if (alg == QD_ALG_TUNNEL) return fail(ctx, QD_ERR_UNSUPPORTED, "QD_ALG_TUNNEL is not built yet");
+  if (alg == QD_ALG_TUNNEL) {
+    if (N < 2) return fail(ctx, QD_ERR_INVALID, "the tunnel-coupled path needs at least 2 dots");
+    if (desc->num_charge_states != 32)
+      return fail(ctx, QD_ERR_UNSUPPORTED, "num_charge_states must be 32 (one basis state per lane), got %d",
+                  desc->num_charge_states);
+    if (NV != G && NV != G + N - 1)
+      return fail(ctx, QD_ERR_INVALID, "tunnel path: n_volt must be n_gate or n_gate + n_dot - 1 (one barrier per gap)");
+    if (NV != G && !cbg) return fail(ctx, QD_ERR_INVALID, "cbg is required when barrier voltages are present");
+  }
   if ((alg == QD_ALG_DEFAULT || alg == QD_ALG_THRESHOLDED) && !cdd_gs)
     return fail(ctx, QD_ERR_INVALID, "cdd_gs is required for the default / thresholded algorithms");
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -342,8 +446,10 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
       r[L.o_spos + j] = sp;
       r[L.o_sneg + j] = sn;
     }
-    if (alg == QD_ALG_TUNNEL && cbg)
-      memcpy(r + L.o_cbg, cbg + (size_t)e * (NV - G) * G, sizeof(double) * (NV - G) * G);
+    if (alg == QD_ALG_TUNNEL) {
+      if (cbg && NV > G) memcpy(r + L.o_cbg, cbg + (size_t)e * (NV - G) * G, sizeof(double) * (NV - G) * G);
+      if (!pack_tunnel_tables(L, r)) return fail(ctx, QD_ERR_INVALID, "env %d: cdd_inv block is singular", e);
+    }
   }
   QD_CUDA(ctx, cudaDeviceSynchronize());   // nothing in flight may still read the old records
   int rc = grow(ctx, &ctx->d_records, &ctx->records_bytes, bytes);

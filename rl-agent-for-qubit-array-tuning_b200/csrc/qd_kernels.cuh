@@ -33,6 +33,7 @@ struct KArgs {
   const double* __restrict__ points;   // [pixels, n_volt] or nullptr (affine scans)
   float* __restrict__ z_out;
   void* __restrict__ n_out;
+  double* __restrict__ nbar;           // tunnel path: <n> per pixel, [pixels, N] (written by qd_tunnel_gs_kernel)
   int n_scan;
   int n_type;
   unsigned flags;
@@ -514,7 +515,7 @@ __global__ void __launch_bounds__(128, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs
     }
     mbar_wait(bar, phase);
     phase ^= 1u;
-    if constexpr (ALG != QD_ALG_BRUTE_FORCE) {
+    if constexpr (ALG == QD_ALG_DEFAULT) {
       if (lane == 0) { pc.meta[0] = 0u; pc.meta[1] = 0u; }    // the projection cache belongs to one env
     }
 
@@ -598,7 +599,12 @@ __global__ void __launch_bounds__(128, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs
           }
 
           // ---- ground state ----
-          if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N>(g, rec, L, kT, nd);
+          if constexpr (ALG == QD_ALG_TUNNEL) {
+            // the tunnel-coupled ground state was computed by qd_tunnel_gs_kernel (one warp per pixel)
+            const double* __restrict__ src = a.nbar + (size_t)(pix0 + pix) * N;
+#pragma unroll
+            for (int j = 0; j < N; ++j) nd[j] = src[j];
+          } else if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N>(g, rec, L, kT, nd);
           else ground_state_box<N>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, nd);
 
           // ---- hysteresis latching along x ----

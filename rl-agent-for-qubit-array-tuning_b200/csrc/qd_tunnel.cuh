@@ -1,0 +1,489 @@
+// qd_tunnel.cuh -- Path B: the tunnel-coupled ground state QADAPT's env.step runs in barrier mode
+// (src/qarray_latched/DotArrays/ground_state.py:24-166; restated in oracle/path_b.py).  sm_100a, one WARP per pixel:
+// the 32-state truncated basis maps one basis state to one lane.
+//
+// Per pixel (all 32 lanes cooperate; pixels of a row are processed in order, so latching and the telegraph chain are
+// plain sequential state):
+//   1. dot potentials g = cgd[:N] v, continuous relaxation (closed form, or the reference's 50 projected-gradient steps).
+//   2. 4^N candidates floor(n_c) + {-1,0,1,2}^N.  E = z^T C z, z = r + delta.  The digits split into a high and a low
+//      half (<= 256 combinations each).  A block = one high combination: its 256 low candidates cost ~8 instructions
+//      each (table of the low quadratic part + 4 FMA of the block-dependent linear part).  Blocks are visited in
+//      increasing order of the Schur-complement lower bound  z_hi^T (Chh - Chl Cll^-1 Clh) z_hi  and the walk stops
+//      when the bound exceeds the current 32nd-best energy: exact, typically 5-20 of 256 blocks at N = 8.
+//      The running top-32 lives one entry per lane; selection order is (energy, index) = the reference's stable sort.
+//   3. H = diag(F) + nearest-neighbour hopping -t_d sqrt(n_from (n_to + 1)), t_d = tc_base exp(-alpha_d vb_eff_d).
+//   4. Ground eigenvector: Householder tridiagonalisation in shared memory (lane = row), lowest eigenvalue bracketed by
+//      32-way multisection on Sturm counts (each lane one shift), inverse iteration on the tridiagonal with the shift
+//      at the lower bracket end (T - mu I is positive definite there: LDL^T without pivoting), back-transformation.
+//   5. <n> = sum_m psi_m^2 n_m is written to a scratch buffer; latching, sensor and noise are then applied by
+//      qd_scan_kernel<N, QD_ALG_TUNNEL> (lane per pixel), so a flat latching pass never serialises the eigen-solves.
+#pragma once
+#include "qd_kernels.cuh"
+
+namespace qd {
+
+constexpr int QD_T_HS = 33;                       // row stride of H in shared memory (bank-conflict free)
+constexpr int QD_T_WORK = 32 * QD_T_HS + 9 * 32 + 64;   // H, dd, ee, e2, qi, ll, yy, vs, qs, spare | small vectors
+
+__host__ __device__ inline int qd_tunnel_slot_bytes(const qd_layout& L) {
+  int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_T_WORK * 8 + 16;
+  return (b + 127) & ~127;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double t = __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), o),
+                                      __shfl_xor_sync(0xffffffffu, __double2loint(v), o));
+    v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, shfl_f64(v, (threadIdx.x & 31) ^ o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, shfl_f64(v, (threadIdx.x & 31) ^ o));
+  return v;
+}
+__device__ __forceinline__ bool lex_less(double e1, int i1, double e2, int i2) {
+  return e1 < e2 || (e1 == e2 && i1 < i2);
+}
+
+// lexicographic (energy, index) maximum over the warp and the lane that holds it
+__device__ __forceinline__ void warp_lex_max(double e, int idx, int lane, double& me, int& mi, int& ml) {
+  me = e; mi = idx; ml = lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oe = shfl_f64(me, lane ^ o);
+    const int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+    const int ol = __shfl_xor_sync(0xffffffffu, ml, o);
+    const bool take = lex_less(me, mi, oe, oi) || (me == oe && mi == oi && ol > ml);
+    if (take) { me = oe; mi = oi; ml = ol; }
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
+  constexpr int NLO = N < 4 ? N : 4;
+  constexpr int NHI = N - NLO;
+  constexpr int NB_LO = 1 << (2 * NLO);            // low candidates per block
+  constexpr int NB_HI = 1 << (2 * NHI);            // blocks
+  constexpr int LO_IT = NB_LO >= 32 ? NB_LO / 32 : 1;
+  constexpr int HI_IT = NB_HI >= 32 ? NB_HI / 32 : 1;
+  constexpr int B = N - 1;
+
+  extern __shared__ __align__(128) unsigned char qd_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int warps_per_cta = blockDim.x >> 5;
+  const qd_layout& L = a.L;
+  const int NV = L.n_volt, G = L.n_gate;
+  const bool barriers = NV > G;
+
+  unsigned char* slot = qd_smem + (size_t)warp * a.slot_bytes;
+  double* rec = reinterpret_cast<double*>(slot);
+  qd_scan* sc = reinterpret_cast<qd_scan*>(slot + (size_t)L.rec_doubles * 8);
+  double* wk = reinterpret_cast<double*>(slot + (size_t)L.rec_doubles * 8 + sizeof(qd_scan));
+  double* H = wk;
+  double* dd = wk + 32 * QD_T_HS;
+  double* ee = dd + 32;
+  double* e2 = ee + 32;
+  double* qi = e2 + 32;
+  double* ll = qi + 32;
+  double* yy = ll + 32;
+  double* vs = yy + 32;
+  double* qs = vs + 32;
+  double* sv = qs + 64;          // small vectors: vv[16] gs[8] ns[8] fs[8] hs[8] ts[8] nb[8]
+  double* vv = sv;
+  double* gs = sv + 16;
+  double* ns = sv + 24;
+  double* fs = sv + 32;
+  double* hs = sv + 40;
+  double* ts = sv + 48;
+  double* nb = sv + 56;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(wk + QD_T_WORK);
+
+  const double* __restrict__ C = rec + L.o_cinv;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+
+  if (lane == 0) mbar_init(bar, 1);
+  __syncwarp();
+  uint32_t phase = 0;
+  const uint32_t rec_bytes = (uint32_t)L.rec_doubles * 8u;
+
+  const long long total_items = (long long)a.n_scan * a.items_per_scan;
+  for (long long item = (long long)blockIdx.x * warps_per_cta + warp; item < total_items;
+       item += (long long)gridDim.x * warps_per_cta) {
+    const int scan_id = (int)(item / a.items_per_scan);
+    const int part = (int)(item - (long long)scan_id * a.items_per_scan);
+    const qd_scan* gscan = a.scans + scan_id;
+    if (lane == 0) {
+      const int env = gscan->env_id;
+      fence_proxy_async();
+      mbar_expect_tx(bar, rec_bytes + (uint32_t)sizeof(qd_scan));
+      tma_bulk_g2s(rec, a.records + (size_t)env * L.rec_doubles, rec_bytes, bar);
+      tma_bulk_g2s(sc, gscan, (uint32_t)sizeof(qd_scan), bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+
+    const int nx = sc->nx, ny = sc->ny;
+    const long long npix = (long long)nx * ny;
+    const long long p_begin = (long long)part * a.rows_per_item;            // rows_per_item = pixels per item here
+    const long long p_end = min(npix, p_begin + (long long)a.rows_per_item);
+    if (p_begin >= npix) { __syncwarp(); continue; }
+
+    const double* par = rec + L.o_par;
+    const bool replace = (a.flags & QD_FLAG_RADIAL) && sc->rad_mode == 2;
+    const long long pix0 = sc->pix_offset;
+
+    {
+      {
+        for (long long pix = p_begin; pix < p_end; ++pix) {
+        const int iy = (int)(pix / nx), ix = (int)(pix - (long long)iy * nx);
+        double nbar[N];
+        if (!replace) {
+          // ---------------- 1. voltages, potentials, tunnel couplings ----------------
+          if (lane < NV) {
+            vv[lane] = (a.points == nullptr)
+                           ? fma((double)iy, sc->dy[lane], fma((double)ix, sc->dx[lane], sc->v0[lane]))
+                           : a.points[(size_t)pix * NV + lane];
+          }
+          __syncwarp();
+          double us = 0.0;
+          {
+            double acc = 0.0;
+            if (lane <= N) {
+              const double* arow = (lane < N) ? rec + L.o_a + lane * NV : rec + L.o_sa;
+              for (int k = 0; k < NV; ++k) acc = fma(arow[k], vv[k], acc);
+            }
+            if (lane < N) gs[lane] = acc;
+            us = shfl_f64(acc, N);
+            if (lane >= 16 && lane < 16 + B) {
+              const int d = lane - 16;
+              double t = par[QD_PAR_TC_BASE];
+              if (barriers) {
+                double vb = vv[G + d];
+                for (int k = 0; k < G; ++k) vb = fma(rec[L.o_cbg + d * G + k], vv[k], vb);
+                t *= exp(-rec[L.o_alpha + d] * vb);
+              }
+              ts[d] = t;
+            }
+          }
+          __syncwarp();
+          // ---------------- continuous relaxation (charge_states.py:36-88) ----------------
+          {
+            const double gj = (lane < N) ? gs[lane] : 0.0;
+            double nj = gj;
+            if (__ballot_sync(0xffffffffu, lane < N && gj < 0.0)) {
+              double cg = 0.0;
+              if (lane < N)
+                for (int k = 0; k < N; ++k) cg = fma(C[lane * N + k], gs[k], cg);
+              nj = fmax(gj, 0.0);
+              for (int it = 0; it < 50; ++it) {
+                if (lane < N) ns[lane] = nj;
+                __syncwarp();
+                if (lane < N) {
+                  double grad = 0.0;
+                  for (int k = 0; k < N; ++k) grad = fma(C[lane * N + k], ns[k], grad);
+                  nj = fmax(nj - 0.1 * (grad - cg), 0.0);
+                }
+                __syncwarp();
+              }
+            }
+            nj = fmax(nj, 0.0);
+            if (lane < N) {
+              const double fj = floor(nj);
+              fs[lane] = fj;
+              ns[lane] = fj - gj;                    // r = f - g
+            }
+          }
+          __syncwarp();
+          if (lane < N) {                            // h = C r
+            double s = 0.0;
+            for (int k = 0; k < N; ++k) s = fma(C[lane * N + k], ns[k], s);
+            hs[lane] = s;
+          }
+          __syncwarp();
+          double f[N], r[N], h[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) { f[j] = fs[j]; r[j] = ns[j]; h[j] = hs[j]; }
+          double E0 = 0.0;
+#pragma unroll
+          for (int j = 0; j < N; ++j) E0 = fma(r[j], h[j], E0);
+
+          // ---------------- 2. streaming top-32 over the 4^N candidates ----------------
+          double le = INF;
+          int lidx = -1;                             // -1: the reference's zero-state padding entry
+          double tau = INF;
+          int tau_idx = -1, tau_lane = 31;
+          // validity of this lane's low candidates and their digit vectors do not depend on the block
+          unsigned lo_valid = 0;
+#pragma unroll
+          for (int i = 0; i < LO_IT; ++i) {
+            const int b = i * 32 + lane;
+            bool ok = b < NB_LO;
+#pragma unroll
+            for (int k = 0; k < NLO; ++k) {
+              const int dg = (b >> (2 * (NLO - 1 - k))) & 3;
+              ok = ok && !(dg == 0 && f[NHI + k] <= 0.0);
+            }
+            lo_valid |= ok ? (1u << i) : 0u;
+          }
+          // lower bounds of this lane's blocks
+          double lb[HI_IT];
+#pragma unroll
+          for (int i = 0; i < HI_IT; ++i) {
+            const int blk = i * 32 + lane;
+            double v = INF;
+            if (blk < NB_HI) {
+              bool ok = true;
+              double zh[NHI > 0 ? NHI : 1];
+#pragma unroll
+              for (int j = 0; j < NHI; ++j) {
+                const int dg = (blk >> (2 * (NHI - 1 - j))) & 3;
+                ok = ok && !(dg == 0 && f[j] <= 0.0);
+                zh[j] = r[j] + (double)(dg - 1);
+              }
+              if (ok) {
+                v = 0.0;
+#pragma unroll
+                for (int p = 0; p < NHI; ++p) {
+                  double s = 0.0;
+#pragma unroll
+                  for (int q = 0; q < NHI; ++q) s = fma(rec[L.o_schur + p * NHI + q], zh[q], s);
+                  v = fma(zh[p], s, v);
+                }
+              }
+            }
+            lb[i] = v;
+          }
+          while (true) {
+            // next unvisited block with the smallest bound
+            double m = INF;
+            int mb = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < HI_IT; ++i)
+              if (lb[i] < m) { m = lb[i]; mb = i * 32 + lane; }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              const double om = shfl_f64(m, lane ^ o);
+              const int ob = __shfl_xor_sync(0xffffffffu, mb, o);
+              if (om < m || (om == m && ob < mb)) { m = om; mb = ob; }
+            }
+            if (!(m < INF)) break;
+            if (m - 1e-12 * (fabs(m) + 1.0) > tau) break;      // every remaining candidate is above the 32nd best
+#pragma unroll
+            for (int i = 0; i < HI_IT; ++i)
+              if (mb == i * 32 + lane) lb[i] = INF;
+            // block constants: base = E0 + 2 x.h_hi + Qhh[x];  c_k = 2 (h_lo[k] + sum_j C[lo k][hi j] x_j)
+            double base = E0 + rec[L.o_qhh + mb];
+            double c[NLO];
+#pragma unroll
+            for (int k = 0; k < NLO; ++k) c[k] = h[NHI + k];
+#pragma unroll
+            for (int j = 0; j < NHI; ++j) {
+              const double xj = (double)(((mb >> (2 * (NHI - 1 - j))) & 3) - 1);
+              base = fma(2.0 * xj, h[j], base);
+#pragma unroll
+              for (int k = 0; k < NLO; ++k) c[k] = fma(C[(NHI + k) * N + j], xj, c[k]);
+            }
+#pragma unroll
+            for (int i = 0; i < LO_IT; ++i) {
+              const int b = i * 32 + lane;
+              const bool ok = (lo_valid >> i) & 1u;
+              double e = INF;
+              if (ok) {
+                e = base + rec[L.o_qll + b];
+#pragma unroll
+                for (int k = 0; k < NLO; ++k) e = fma(2.0 * (double)(((b >> (2 * (NLO - 1 - k))) & 3) - 1), c[k], e);
+              }
+              const int cidx = mb * NB_LO + b;
+              unsigned pm = __ballot_sync(0xffffffffu, ok && lex_less(e, cidx, tau, tau_idx));
+              while (pm) {
+                const int p = __ffs(pm) - 1;
+                pm &= pm - 1u;
+                const double pe = shfl_f64(e, p);
+                const int pi = __shfl_sync(0xffffffffu, cidx, p);
+                if (lex_less(pe, pi, tau, tau_idx)) {
+                  if (lane == tau_lane) { le = pe; lidx = pi; }
+                  warp_lex_max(le, lidx, lane, tau, tau_idx, tau_lane);
+                }
+              }
+            }
+          }
+
+          // ---------------- 3. basis states, free energies, Hamiltonian ----------------
+          double st[N];
+          uint64_t key = 0;
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            st[j] = (lidx < 0) ? 0.0 : f[j] + (double)(((lidx >> (2 * (N - 1 - j))) & 3) - 1);
+            key |= (uint64_t)((unsigned)(int)st[j] & 0xffu) << (8 * j);
+          }
+          double Fm = 0.0;
+          {
+            double zz[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) zz[j] = st[j] - gs[j];
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              double s = 0.0;
+#pragma unroll
+              for (int j = 0; j < N; ++j) s = fma(C[i * N + j], zz[j], s);
+              Fm = fma(zz[i], s, Fm);
+            }
+          }
+          for (int j = 0; j < 32; ++j) {
+            const uint64_t kj = shfl_u64(key, j);
+            double val = (j == lane) ? Fm : 0.0;
+            // per-byte difference kj - key (SWAR, no carries across bytes)
+            const uint64_t Hm = 0x8080808080808080ULL;
+            const uint64_t d = ((kj | Hm) - (key & ~Hm)) ^ ((kj ^ ~key) & Hm);
+            const uint64_t nz = (((d & ~Hm) + ~Hm) | d) & Hm;
+            if (__popcll(nz) == 2) {
+              const int p0 = (__ffsll((long long)nz) - 1) >> 3;
+              const int p1 = (63 - __clzll((long long)nz)) >> 3;
+              if (p1 == p0 + 1) {
+                const unsigned b0 = (unsigned)(d >> (8 * p0)) & 0xffu, b1 = (unsigned)(d >> (8 * p1)) & 0xffu;
+                const double n0 = (double)((unsigned)(key >> (8 * p0)) & 0xffu);
+                const double n1 = (double)((unsigned)(key >> (8 * p1)) & 0xffu);
+                if (b0 == 0xffu && b1 == 0x01u) val = -ts[p0] * sqrt(n0 * (n1 + 1.0));        // hop p0 -> p0+1
+                else if (b0 == 0x01u && b1 == 0xffu) val = -ts[p0] * sqrt(n1 * (n0 + 1.0));   // hop p0+1 -> p0
+              }
+            }
+            H[lane * QD_T_HS + j] = val;
+          }
+          __syncwarp();
+
+          // ---------------- 4. ground eigenvector ----------------
+          for (int k = 0; k < 30; ++k) {
+            const double x = (lane > k) ? H[lane * QD_T_HS + k] : 0.0;
+            const double xk1 = shfl_f64(x, k + 1);
+            const double sig = warp_sum((lane > k + 1) ? x * x : 0.0);
+            if (sig == 0.0) {
+              if (lane == 0) ee[k] = xk1;
+              if (lane > k) H[lane * QD_T_HS + k] = 0.0;
+              __syncwarp();
+              continue;
+            }
+            const double norm2 = sig + xk1 * xk1;
+            const double alpha = (xk1 > 0.0) ? -sqrt(norm2) : sqrt(norm2);
+            double v = x;
+            if (lane == k + 1) v -= alpha;
+            const double vn2 = 2.0 * (norm2 - alpha * xk1);
+            v *= rsqrt(vn2);
+            vs[lane] = v;
+            __syncwarp();
+            double p = 0.0;
+            if (lane > k)
+              for (int j = k + 1; j < 32; ++j) p = fma(H[lane * QD_T_HS + j], vs[j], p);
+            const double K = warp_sum(v * p);
+            const double q = p - K * v;
+            qs[lane] = q;
+            __syncwarp();
+            if (lane > k) {
+              for (int j = k + 1; j < 32; ++j)
+                H[lane * QD_T_HS + j] -= 2.0 * fma(v, qs[j], q * vs[j]);
+              H[lane * QD_T_HS + k] = v;                       // the dead column keeps the reflector
+            }
+            if (lane == 0) ee[k] = alpha;
+            __syncwarp();
+          }
+          dd[lane] = H[lane * QD_T_HS + lane];
+          if (lane == 0) { ee[30] = H[31 * QD_T_HS + 30]; ee[31] = 0.0; }
+          __syncwarp();
+          e2[lane] = ee[lane] * ee[lane];
+          double lo, hi;
+          {
+            const double rad = ((lane > 0) ? fabs(ee[lane - 1]) : 0.0) + ((lane < 31) ? fabs(ee[lane]) : 0.0);
+            lo = warp_min(dd[lane] - rad);
+            hi = warp_max(dd[lane] + rad);
+          }
+          __syncwarp();
+          for (int round = 0; round < 7; ++round) {
+            const double x = fma((double)(lane + 1) * (1.0 / 33.0), hi - lo, lo);
+            double q = dd[0] - x;
+            if (q == 0.0) q = 1e-300;
+            int cnt = q < 0.0;
+            for (int i = 1; i < 32; ++i) {
+              q = (dd[i] - x) - e2[i - 1] * __drcp_rn(q);
+              if (q == 0.0) q = 1e-300;
+              cnt += q < 0.0;
+            }
+            const unsigned mm = __ballot_sync(0xffffffffu, cnt >= 1);
+            const int j = mm ? __ffs(mm) - 1 : 32;
+            const double xl = shfl_f64(x, (j > 0) ? j - 1 : 0);
+            const double xh = shfl_f64(x, (j < 32) ? j : 31);
+            if (j > 0) lo = xl;
+            if (j < 32) hi = xh;
+          }
+          const double mu = lo;
+          if (lane == 0) {
+            double q = dd[0] - mu;
+            for (int i = 0; i < 31; ++i) {
+              if (!(q > 0.0)) q = 1e-300;
+              const double iq = 1.0 / q;
+              qi[i] = iq;
+              const double l = ee[i] * iq;
+              ll[i] = l;
+              q = (dd[i + 1] - mu) - l * ee[i];
+            }
+            if (!(q > 0.0)) q = 1e-300;
+            qi[31] = 1.0 / q;
+          }
+          yy[lane] = 1.0 + (double)lane * (1.0 / 64.0);
+          __syncwarp();
+          for (int it = 0; it < 5; ++it) {
+            if (lane == 0) {
+              double zprev = yy[0];
+              for (int i = 1; i < 32; ++i) { zprev = yy[i] - ll[i - 1] * zprev; yy[i] = zprev; }
+              double ynext = yy[31] * qi[31];
+              yy[31] = ynext;
+              for (int i = 30; i >= 0; --i) { ynext = yy[i] * qi[i] - ll[i] * ynext; yy[i] = ynext; }
+            }
+            __syncwarp();
+            double yv = yy[lane];
+            // scale first (the unnormalised iterate can overflow when mu is within rounding of lambda_0)
+            const double ymax = warp_max(fabs(yv));
+            yv *= 1.0 / ymax;
+            const double nrm = warp_sum(yv * yv);
+            yy[lane] = yv * rsqrt(nrm);
+            __syncwarp();
+          }
+          double psi = yy[lane];
+          for (int k = 29; k >= 0; --k) {
+            const double v = (lane > k) ? H[lane * QD_T_HS + k] : 0.0;
+            const double dot = warp_sum(v * psi);
+            psi = fma(-2.0 * dot, v, psi);
+          }
+          {
+            const double w2 = psi * psi;
+#pragma unroll
+            for (int j = 0; j < N; ++j) nbar[j] = warp_sum(w2 * st[j]);
+          }
+
+        } else {
+#pragma unroll
+          for (int j = 0; j < N; ++j) nbar[j] = 0.0;
+        }
+        // ---------------- <n> -> scratch ----------------
+        if (lane == 0) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) nb[j] = nbar[j];
+        }
+        __syncwarp();
+        if (lane < N) a.nbar[(pix0 + pix) * N + lane] = nb[lane];
+        __syncwarp();
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace qd

@@ -83,6 +83,31 @@ class ModelBatch:
                    cdd_inv_full=cdd_inv_full, cgd_full=cgd_full, params=params)
 
 
+def tunnel_model_batch(Cdd, Cgd, Cds, Cgs, Cbd, Cbg, Cbs, tc_base, alpha, p_leads=None, p_inter=None, white_amp=0.0,
+                       tele_p01=0.0, tele_p10=0.0, tele_amp=0.0, num_charge_states: int = 32,
+                       charge_state_batch_size: int = 1000) -> ModelBatch:
+    """Path B (``TunnelCoupledChargeSensed`` with barriers) batch from non-Maxwell matrices with a leading env axis.
+    Barriers are voltage sources: extra columns of cgd (src/qarray_latched/DotArrays/_helper_functions.py:60-126); the
+    ground state uses the dot block of the FULL inverse (ground_state.py:60-65)."""
+    Cdd, Cgd, Cds, Cgs, Cbd, Cbg, Cbs = (np.asarray(a, dtype=np.float64) for a in (Cdd, Cgd, Cds, Cgs, Cbd, Cbg, Cbs))
+    n_env, n_dot, n_barrier = Cdd.shape[0], Cdd.shape[-1], Cbd.shape[-1]
+    cdd_nm, cgd_nm = maxwell.embed_sensor(Cdd, Cgd, Cds, Cgs, Cbd, Cbs)
+    _, cdd_inv_full, cgd_full = maxwell.maxwell(cdd_nm, cgd_nm)
+    params = np.zeros(n_env, dtype=PARAMS_DTYPE)
+    params["white_amp"], params["tele_p01"], params["tele_p10"], params["tele_amp"] = white_amp, tele_p01, tele_p10, tele_amp
+    params["tc_base"] = tc_base
+    params["alpha"][:, :n_barrier] = np.broadcast_to(np.asarray(alpha, dtype=np.float64), (n_env, n_barrier))
+    if p_leads is not None:
+        params["latching"] = 1
+        params["p_leads"][:, :n_dot] = np.broadcast_to(np.asarray(p_leads, dtype=np.float64), (n_env, n_dot))
+        pin = np.zeros((n_env, QD_MAX_DOTS, QD_MAX_DOTS))
+        pin[:, :n_dot, :n_dot] = np.broadcast_to(np.asarray(p_inter, dtype=np.float64), (n_env, n_dot, n_dot))
+        params["p_inter"] = pin.reshape(n_env, -1)
+    return ModelBatch(algorithm="tunnel", n_gate=Cgd.shape[-1], cdd_inv_gs=np.ascontiguousarray(cdd_inv_full[:, :n_dot, :n_dot]),
+                      cdd_gs=None, cdd_inv_full=cdd_inv_full, cgd_full=cgd_full, params=params, cbg=Cbg,
+                      num_charge_states=num_charge_states, charge_state_batch_size=charge_state_batch_size)
+
+
 def new_scans(n: int) -> np.ndarray:
     """Zero-initialised array of ``n`` scan descriptors (``qd_scan``)."""
     s = np.zeros(n, dtype=SCAN_DTYPE)

@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import maxwell
-from .engine import ModelBatch, new_scans
+from .engine import ModelBatch, new_scans, tunnel_model_batch
 
 
 def _by_distance(rng, n_env, n_rows, n_cols, ranges, offset=0.0):
@@ -65,6 +65,30 @@ def model_batch(dev: dict, algorithm: str = "default", thermal: bool = False, la
         tele_p10=dev["tele_p10"] if noise else 0.0, tele_amp=dev["tele_amp"] if noise else 0.0)
 
 
+def sample_barrier_devices(n_env: int, n_dot: int, seed: int = 1234):
+    """``sample_devices`` plus the barrier matrices and the barrier-voltage model of the tunnel-coupled path
+    (qarray_config.yaml:72-100; qarray_base_class.py:300-357, 521-534)."""
+    dev = sample_devices(n_env, n_dot, seed)
+    rng = np.random.default_rng([seed, 77])
+    N, B, G = n_dot, n_dot - 1, n_dot + 1
+    dev["Cbd"] = _by_distance(rng, n_env, N, B, [(0.04, 0.08), (0.04, 0.08), (0.01, 0.03), (0.005, 0.015)], offset=0.5)
+    cbg = _by_distance(rng, n_env, G, B, [(0.08, 0.15), (0.08, 0.15), (0.03, 0.18), (0.01, 0.03)], offset=0.5)
+    cbg[:, N, :] = rng.uniform(0.03, 0.18, size=(n_env, B))                 # sensor gate: the distance-2 rule
+    dev["Cbg"] = np.ascontiguousarray(np.swapaxes(cbg, -1, -2))              # (E, B, G)
+    dev["Cbs"] = rng.uniform(3e-4, 1e-3, size=(n_env, 1, B))
+    dev["tc_base"] = rng.uniform(0.5, 3.0, n_env)
+    dev["alpha"] = rng.uniform(0.8, 2.0, size=(n_env, B))
+    return dev
+
+
+def tunnel_batch(dev: dict, latching: bool = True, noise: bool = True) -> ModelBatch:
+    return tunnel_model_batch(
+        dev["Cdd"], dev["Cgd"], dev["Cds"], dev["Cgs"], dev["Cbd"], dev["Cbg"], dev["Cbs"], dev["tc_base"], dev["alpha"],
+        p_leads=dev["p_leads"] if latching else None, p_inter=dev["p_inter"] if latching else None,
+        white_amp=dev["white_amp"] if noise else 0.0, tele_p01=dev["tele_p01"] if noise else 0.0,
+        tele_p10=dev["tele_p10"] if noise else 0.0, tele_amp=dev["tele_amp"] if noise else 0.0)
+
+
 def ground_truth(mb: ModelBatch, dots: float = 1.0, sensor: float = 0.53):
     """Gate voltages (E, G) that put every dot at ``dots`` carriers and the sensor at ``sensor``."""
     n = np.concatenate([np.full(mb.n_dot, dots), [sensor]])
@@ -96,6 +120,9 @@ def env_step_scans(mb: ModelBatch, dev: dict, res: int = 64, seed: int = 7, offs
     v0[rows, ch] = centre[env, ch] - half[env]
     v0[rows, ch + 1] = centre[env, ch + 1] - half[env]
     scans["v0"][:, :G] = -v0
+    if mb.n_volt > G:                                     # tunnel path: barrier voltages ride along, constant per scan
+        vb = rng.uniform(-1.0, 3.0, size=(E, mb.n_volt - G))
+        scans["v0"][:, G:mb.n_volt] = vb[env]
     scans["dx"][rows, ch] = -step_v
     scans["dy"][rows, ch + 1] = -step_v
     scans["peak_width"] = dev["peak_width"][env]

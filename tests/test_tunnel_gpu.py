@@ -1,0 +1,94 @@
+"""Path B on the GPU (QD_ALG_TUNNEL: what QADAPT's env.step runs in barrier mode) against the literal NumPy restatement
+of src/qarray_latched/DotArrays/ground_state.py (oracle/path_b.py).
+
+<n> is an eigenvector expectation: it is compared within 1e-6 absolute wherever the pixel's spectral gap exceeds 1e-5
+(below that the ground vector itself is ill-conditioned: LAPACK and any other solver legitimately differ)."""
+import numpy as np
+import pytest
+
+from util import oracle_batch
+
+pytestmark = pytest.mark.gpu
+
+N_ATOL = 1e-6
+GAP_MIN = 1e-5
+
+
+def _setup(engine, n_dot, n_env, res, seed, **kw):
+    from qdsim import synth
+    dev = synth.sample_barrier_devices(n_env, n_dot, seed=seed)
+    mb = synth.tunnel_batch(dev, **kw)
+    engine.set_models(mb)
+    scans = synth.env_step_scans(mb, dev, res=res, seed=seed + 1, offset_range=2.5)
+    return dev, mb, scans
+
+
+@pytest.mark.parametrize("n_dot,res,n_env", [(4, 32, 2), (5, 24, 1), (6, 16, 1), (8, 8, 1)])
+def test_tunnel_ground_state_matches_oracle(engine, n_dot, res, n_env):
+    from qdsim import N_F64
+    dev, mb, scans = _setup(engine, n_dot, n_env, res, seed=20 + n_dot, latching=False, noise=False)
+    scans = scans[: min(len(scans), 3)].copy()
+    scans["pix_offset"] = np.arange(len(scans)) * res * res
+    z, n = engine.scan_open_host(scans, n_type=N_F64, flags=0)
+    z_ref, n_ref, gap = oracle_batch(mb, scans, 0)
+    z, n = z.reshape(z_ref.shape), n.reshape(n_ref.shape)
+    ok = gap > GAP_MIN
+    assert ok.mean() > 0.9
+    assert np.isfinite(n).all() and np.isfinite(z).all()
+    np.testing.assert_allclose(n[ok], n_ref[ok], rtol=0, atol=N_ATOL)
+    np.testing.assert_allclose(z[ok], z_ref[ok], rtol=1e-5, atol=1e-7)
+    assert (np.abs(n_ref - np.rint(n_ref)) > 0.05).any(), "tunnel coupling should smear some transitions"
+
+
+def test_tunnel_with_latching_and_noise(engine):
+    from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_F64
+    flags = FLAG_LATCH | FLAG_NOISE | FLAG_RADIAL
+    dev, mb, scans = _setup(engine, 4, 2, 24, seed=31)
+    scans["rad_zero_radius"], scans["rad_alpha"] = 1.0, 0.02
+    z, n = engine.scan_open_host(scans, n_type=N_F64, flags=flags)
+    z_ref, n_ref, gap = oracle_batch(mb, scans, flags)
+    z, n = z.reshape(z_ref.shape), n.reshape(n_ref.shape)
+    # a rounded-compare latch decision can flip when <n> sits within 1e-6 of a half-integer: require agreement on
+    # all but a handful of pixels, exact agreement elsewhere
+    bad = np.abs(n - n_ref).max(axis=-1) > N_ATOL
+    assert bad.mean() < 0.01, f"{bad.sum()} of {bad.size} pixels differ"
+    np.testing.assert_allclose(z[~bad], z_ref[~bad], rtol=0, atol=5e-6)
+
+
+def test_tunnel_points_mode_flat_pass(engine):
+    """The facade's barrier-mode call: charge_sensor_open(vg_flat (P, G), vb (P, B)) -- one row of P points."""
+    from oracle import composer
+    from qdsim import FLAG_LATCH, N_F64
+    dev, mb, scans = _setup(engine, 4, 1, 16, seed=41, noise=False)
+    rec = scans[0]
+    nv = mb.n_volt
+    v = composer.affine_grid(rec["v0"][:nv], rec["dx"][:nv], rec["dy"][:nv], 16, 16).reshape(1, 256, nv)
+    z, n = engine.points_open_host(rec, v, n_type=N_F64, flags=FLAG_LATCH)
+    flat = scans[:1].copy()
+    from qdsim import FLAG_CARRY_ROWS
+    z_ref, n_ref, gap = oracle_batch(mb, flat, FLAG_LATCH | FLAG_CARRY_ROWS)
+    bad = np.abs(n.reshape(16, 16, -1) - n_ref[0]).max(axis=-1) > N_ATOL
+    assert bad.mean() < 0.02
+    np.testing.assert_allclose(z.reshape(16, 16)[~bad], z_ref[0][~bad], rtol=1e-5, atol=1e-7)
+
+
+def test_tunnel_constant_tc_without_barriers(engine):
+    """No barrier voltages: constant nearest-neighbour coupling model.tc (ground_state.py:92-101); tc -> 0 recovers the
+    integer argmin over the kept states (SURVEY.md section 8c test 5)."""
+    from qdsim import N_F64, synth
+    from qdsim.engine import ModelBatch, PARAMS_DTYPE
+    from qdsim import maxwell
+    dev = synth.sample_devices(1, 4, seed=51)
+    cdd_nm, cgd_nm = maxwell.embed_sensor(dev["Cdd"], dev["Cgd"], dev["Cds"], dev["Cgs"])
+    _, cdi_f, cgd_f = maxwell.maxwell(cdd_nm, cgd_nm)
+    params = np.zeros(1, dtype=PARAMS_DTYPE)
+    params["tc_base"] = 1e-9
+    mb = ModelBatch(algorithm="tunnel", n_gate=5, cdd_inv_gs=np.ascontiguousarray(cdi_f[:, :4, :4]), cdd_gs=None,
+                    cdd_inv_full=cdi_f, cgd_full=cgd_f, params=params)
+    engine.set_models(mb)
+    scans = synth.env_step_scans(mb, dev, res=24, seed=52, offset_range=2.0, radial=False)[:1]
+    z, n = engine.scan_open_host(scans, n_type=N_F64, flags=0)
+    z_ref, n_ref, gap = oracle_batch(mb, scans, 0)
+    ok = gap.reshape(-1) > 1e-4
+    assert np.abs(n[ok] - np.rint(n[ok])).max() < 1e-6, "t -> 0: occupations are integers away from degeneracies"
+    np.testing.assert_allclose(n[ok], n_ref.reshape(-1, 4)[ok], rtol=0, atol=N_ATOL)

@@ -21,7 +21,9 @@ def oracle_model(mb, e: int, flags: int = 0):
         p_leads=p["p_leads"][:n].copy(), p_inter=p["p_inter"].reshape(8, 8)[:n, :n].copy(),
         white_amp=float(p["white_amp"]) if noise else 0.0, tele_p01=float(p["tele_p01"]),
         tele_p10=float(p["tele_p10"]), tele_amp=float(p["tele_amp"]) if noise else 0.0,
-        n_gate=mb.n_gate)
+        n_gate=mb.n_gate, cbg=None if mb.cbg is None else mb.cbg[e], tc_base=float(p["tc_base"]),
+        alpha=p["alpha"].copy(), num_charge_states=mb.num_charge_states,
+        charge_state_batch_size=mb.charge_state_batch_size)
 
 
 def oracle_scan(rec, n_volt: int, flags: int = 0):
