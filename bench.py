@@ -163,10 +163,14 @@ def cpu_reference_pixels_per_s(mb, scans, flags, n_sample_scans: int, cores: int
     return pixels / dt, pixels, dt, "port: NumPy restatement, one process per core"
 
 
-def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int):
+def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int, path: str = "A"):
     from qdsim import synth
-    dev = synth.sample_devices(n_env, n_dot, seed=1234 + rank)
-    mb = synth.model_batch(dev, algorithm="default", thermal=False, latching=True, noise=True)
+    if path == "B":
+        dev = synth.sample_barrier_devices(n_env, n_dot, seed=1234 + rank)
+        mb = synth.tunnel_batch(dev, latching=True, noise=True)
+    else:
+        dev = synth.sample_devices(n_env, n_dot, seed=1234 + rank)
+        mb = synth.model_batch(dev, algorithm="default", thermal=False, latching=True, noise=True)
     sets = [synth.env_step_scans(mb, dev, res=res, seed=99 + rank, step=s) for s in range(n_sets)]
     return dev, mb, sets
 
@@ -182,6 +186,9 @@ def main():
     ap.add_argument("--res", type=int, default=64)
     ap.add_argument("--cpu-scans", type=int, default=0, help="scans in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--path", default="A", choices=["A", "B"],
+                    help="A: constant-interaction ChargeSensedDotArray path (headline); B: tunnel-coupled path of "
+                         "env.step in barrier mode (secondary; use e.g. --n-dot 4 --n-env 1024)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -195,6 +202,9 @@ def main():
     pix_per_env = (N - 1) * res * res
     workload = (f"{N}-dot latched array, {args.n_env} envs/GPU, {N - 1} scans/env of {res}x{res}, default algorithm, "
                 f"T=0, latching + white/telegraph/radial noise")
+    if args.path == "B":
+        workload = (f"{N}-dot tunnel-coupled array (32-state basis, barrier voltages), {args.n_env} envs/GPU, {N - 1} "
+                    f"scans/env of {res}x{res}, latching + white/telegraph/radial noise")
     config = {"workload": workload, "n_dot": N, "n_env_per_gpu": args.n_env, "res": res,
               "scans_per_env": N - 1, "l2": "inputs+outputs per step >> L2 (outputs alone 12 B/pixel)"}
 
@@ -239,13 +249,15 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
     n_sets = 2
-    dev, mb, sets = build_workload(args.n_env, N, res, rank, n_sets)
+    dev, mb, sets = build_workload(args.n_env, N, res, rank, n_sets, args.path)
     eng.set_models(mb)
     n_scan = len(sets[0])
     pixels = n_scan * res * res
     stream = torch.cuda.current_stream()
     z_dev = torch.empty(pixels, dtype=torch.float32, device="cuda")
     n_dev = torch.empty((pixels, N), dtype=torch.uint8, device="cuda")
+    if args.path == "B":
+        n_dev = torch.empty((pixels, N), dtype=torch.float32, device="cuda")
 
     def barrier():
         if world > 1:
@@ -261,8 +273,12 @@ def main():
 
     # ---- (1) device-resident timing: `value` and the kernel's roofline ----
     eng.scan_upload(sets[0], stream)
+    N_OUT = N_U8
+    if args.path == "B":
+        from qdsim import N_F32
+        N_OUT = N_F32
     for _ in range(warmup):
-        eng.scan_launch(z_dev, n_dev, N_U8, flags, stream)
+        eng.scan_launch(z_dev, n_dev, N_OUT, flags, stream)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -271,7 +287,7 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev[0].record(stream)
     for k in range(args.steps):
-        eng.scan_launch(z_dev, n_dev, N_U8, flags, stream)
+        eng.scan_launch(z_dev, n_dev, N_OUT, flags, stream)
         ev[k + 1].record(stream)
     barrier()
     launches = eng.launch_count - launches0
@@ -280,7 +296,7 @@ def main():
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     ms_per_step = total_ms / args.steps
     value = world * pixels / (ms_per_step * 1e-3)
-    checksum = int(n_dev[:: max(1, pixels // 4096)].sum().item())
+    checksum = float(n_dev[:: max(1, pixels // 4096)].double().sum().item())
 
     # ---- (2) end to end through the host-buffer path ----
     pinned_scans = [torch.empty(s.nbytes, dtype=torch.uint8).pin_memory() for s in sets]
@@ -334,7 +350,11 @@ def main():
                     "algorithmic_bytes_per_pixel": bytes_per_pixel},
         }
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if args.path == "B":
+            roofline.update({"kernel": f"qd_tunnel_gs_kernel<{N}> + qd_scan_kernel<{N},tunnel>", "achieved": None,
+                             "frac": None, "flop_per_pixel": None, "pipe_slot_frac": None,
+                             "note": "secondary path: no flop model yet; see profiles/"})
+        if world == 1 and not args.no_cpu_baseline and args.path == "A":
             cores = os.cpu_count() or 1
             pps, cpix, cdt, kind = cpu_reference_pixels_per_s(mb, sets[0], flags, args.cpu_scans, cores)
             cpu = {"value": pps, "unit": "pixels/s", "cores": cores, "kind": "port",

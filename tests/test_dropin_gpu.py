@@ -93,3 +93,43 @@ def test_noise_and_latching_models_are_honoured_and_seedable():
     thermal.T = 100.0
     nt = thermal.ground_state_open(np.array([[-0.52, -0.5, 0.0]]))
     assert nt.shape == (1, 2)
+
+
+def test_tunnel_coupled_class_as_the_facade_calls_it():
+    """qarray_base_class.py:817-838 constructor kwargs and :143-163 call pattern: composer.do2d('vP1', ..., 'vP2', ...,
+    gate_voltages, True) -> flatten -> charge_sensor_open(vg_flat, vb)."""
+    import qarray
+    from oracle import capacitance as ocap
+    from oracle import path_b, sensor
+    from oracle import scan as oscan
+    from qarray_latched.DotArrays.barrier_voltage_model import BarrierVoltageModel
+    from qarray_latched.DotArrays.TunnelCoupledChargeSensed import TunnelCoupledChargeSensed
+    from qdsim import synth
+    dev = synth.sample_barrier_devices(1, 4, seed=61)
+    raw = {k: dev[k][0] for k in ("Cdd", "Cgd", "Cds", "Cgs", "Cbd", "Cbg", "Cbs")}
+    bm = BarrierVoltageModel(n_barrier=3, n_dot=4, tc_base=float(dev["tc_base"][0]), alpha=list(dev["alpha"][0]))
+    m = TunnelCoupledChargeSensed(**raw, Cbb=np.eye(3), barrier_model=bm, coulomb_peak_width=0.2, T=100.0,
+                                  max_charge_carriers=4, tc=0.15, noise_model=None, latching_model=None,
+                                  voltage_capacitance_model=None, use_sparse=False, num_charge_states=32,
+                                  charge_state_batch_size=1000, charge_carrier="electrons")
+    res = 24
+    m.gate_voltage_composer.virtual_gate_matrix = -np.eye(5)
+    gv = np.array([0.6, 0.9, 0.4, 0.7, 0.5])
+    vg = m.gate_voltage_composer.do2d("vP1", gv[0] - 1.5, gv[0] + 1.5, res, "vP2", gv[1] - 1.5, gv[1] + 1.5, res, gv, True)
+    vg_flat = vg.reshape(-1, vg.shape[-1])
+    vb = np.full((vg_flat.shape[0], 3), np.array([1.5, 2.0, 0.5]))
+    z, n = m.charge_sensor_open(vg_flat, vb)
+    assert z.shape == (res * res, 1) and n.shape == (res * res, 4)
+    # oracle on the same explicit voltages
+    _, cdi_f, cgd_f = ocap.with_barriers_and_sensor(raw["Cdd"], raw["Cgd"], raw["Cds"], raw["Cgs"], raw["Cbd"], raw["Cbs"])
+    om = oscan.Model(cdd_inv=cdi_f[:4, :4], cdd=None, cgd=cgd_f[:4], cdd_inv_full=cdi_f, cgd_full=cgd_f,
+                     algorithm="tunnel", n_gate=5, cbg=raw["Cbg"], tc_base=bm.tc_base, alpha=np.asarray(bm.alpha))
+    v_ext = np.concatenate([vg_flat, vb], axis=1)
+    n_ref, gap = path_b.ground_state_open(om, v_ext, return_gap=True)
+    ok = gap > 1e-5
+    assert ok.mean() > 0.9
+    np.testing.assert_allclose(n[ok], n_ref[ok], rtol=0, atol=1e-6)
+    z_ref = sensor.charge_sensor_signal(n_ref, v_ext, cdi_f, cgd_f, 0.2)
+    np.testing.assert_allclose(z[ok], z_ref[ok], rtol=1e-5, atol=1e-7)
+    with pytest.raises(ValueError):
+        m.charge_sensor_open(vg_flat)            # barrier voltages are required for a model built with barriers
