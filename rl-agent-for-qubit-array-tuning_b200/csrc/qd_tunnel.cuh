@@ -95,8 +95,8 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
   double* qi = e2 + 32;
   double* ll = qi + 32;
   double* yy = ll + 32;
-  double* vs = yy + 32;
-  double* qs = vs + 32;
+  double* vq = yy + 32;          // interleaved (v_j, q_j) of the current Householder step, 64 doubles
+  double* qs = vq + 32;
   double* sv = qs + 64;          // small vectors: vv[16] gs[8] ns[8] fs[8] hs[8] ts[8] nb[8]
   double* vv = sv;
   double* gs = sv + 16;
@@ -217,10 +217,11 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           for (int j = 0; j < N; ++j) E0 = fma(r[j], h[j], E0);
 
           // ---------------- 2. streaming top-32 over the 4^N candidates ----------------
+          // lane l holds the l-th smallest (energy, index) seen so far; tau = lane 31's entry, replicated in every lane
           double le = INF;
           int lidx = -1;                             // -1: the reference's zero-state padding entry
           double tau = INF;
-          int tau_idx = -1, tau_lane = 31;
+          int tau_idx = 0x7fffffff;
           // validity of this lane's low candidates and their digit vectors do not depend on the block
           unsigned lo_valid = 0;
 #pragma unroll
@@ -292,7 +293,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
 #pragma unroll
               for (int k = 0; k < NLO; ++k) c[k] = fma(C[(NHI + k) * N + j], xj, c[k]);
             }
-#pragma unroll
+#pragma unroll 1
             for (int i = 0; i < LO_IT; ++i) {
               const int b = i * 32 + lane;
               const bool ok = (lo_valid >> i) & 1u;
@@ -310,8 +311,16 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
                 const double pe = shfl_f64(e, p);
                 const int pi = __shfl_sync(0xffffffffu, cidx, p);
                 if (lex_less(pe, pi, tau, tau_idx)) {
-                  if (lane == tau_lane) { le = pe; lidx = pi; }
-                  warp_lex_max(le, lidx, lane, tau, tau_idx, tau_lane);
+                  // sorted insert: entries not below the newcomer move one lane up, the last one drops out
+                  const unsigned below = __ballot_sync(0xffffffffu, lex_less(le, lidx, pe, pi));
+                  const int pos = __popc(below);
+                  const double ue = shfl_f64(le, (lane > 0) ? lane - 1 : 0);
+                  const int ui = __shfl_sync(0xffffffffu, lidx, (lane > 0) ? lane - 1 : 0);
+                  if (lane > pos) { le = ue; lidx = ui; }
+                  else if (lane == pos) { le = pe; lidx = pi; }
+                  tau = shfl_f64(le, 31);
+                  tau_idx = __shfl_sync(0xffffffffu, lidx, 31);
+                  if (!(tau < INF)) tau_idx = 0x7fffffff;      // padding entries lose against every real candidate
                 }
               }
             }
@@ -338,6 +347,14 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               Fm = fma(zz[i], s, Fm);
             }
           }
+          // hopping amplitudes out of this lane's state, one square root per (bond, direction)
+          double amp_f[B], amp_b[B];
+#pragma unroll
+          for (int d = 0; d < B; ++d) {
+            amp_f[d] = -ts[d] * sqrt(st[d] * (st[d + 1] + 1.0));        // d -> d+1
+            amp_b[d] = -ts[d] * sqrt(st[d + 1] * (st[d] + 1.0));        // d+1 -> d
+          }
+#pragma unroll 1
           for (int j = 0; j < 32; ++j) {
             const uint64_t kj = shfl_u64(key, j);
             double val = (j == lane) ? Fm : 0.0;
@@ -350,10 +367,12 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               const int p1 = (63 - __clzll((long long)nz)) >> 3;
               if (p1 == p0 + 1) {
                 const unsigned b0 = (unsigned)(d >> (8 * p0)) & 0xffu, b1 = (unsigned)(d >> (8 * p1)) & 0xffu;
-                const double n0 = (double)((unsigned)(key >> (8 * p0)) & 0xffu);
-                const double n1 = (double)((unsigned)(key >> (8 * p1)) & 0xffu);
-                if (b0 == 0xffu && b1 == 0x01u) val = -ts[p0] * sqrt(n0 * (n1 + 1.0));        // hop p0 -> p0+1
-                else if (b0 == 0x01u && b1 == 0xffu) val = -ts[p0] * sqrt(n1 * (n0 + 1.0));   // hop p0+1 -> p0
+                const bool fwd = b0 == 0xffu && b1 == 0x01u, bwd = b0 == 0x01u && b1 == 0xffu;
+                if (fwd || bwd) {
+#pragma unroll
+                  for (int dd_ = 0; dd_ < B; ++dd_)
+                    if (p0 == dd_) val = fwd ? amp_f[dd_] : amp_b[dd_];
+                }
               }
             }
             H[lane * QD_T_HS + j] = val;
@@ -377,19 +396,32 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
             if (lane == k + 1) v -= alpha;
             const double vn2 = 2.0 * (norm2 - alpha * xk1);
             v *= rsqrt(vn2);
-            vs[lane] = v;
+            vq[2 * lane] = v;
             __syncwarp();
             double p = 0.0;
-            if (lane > k)
-              for (int j = k + 1; j < 32; ++j) p = fma(H[lane * QD_T_HS + j], vs[j], p);
+            if (lane > k) {
+              double p0 = 0.0, p1 = 0.0;
+              const double* __restrict__ hrow = H + lane * QD_T_HS;
+              int j = k + 1;
+              for (; j + 1 < 32; j += 2) {
+                p0 = fma(hrow[j], vq[2 * j], p0);
+                p1 = fma(hrow[j + 1], vq[2 * j + 2], p1);
+              }
+              if (j < 32) p0 = fma(hrow[j], vq[2 * j], p0);
+              p = p0 + p1;
+            }
             const double K = warp_sum(v * p);
             const double q = p - K * v;
-            qs[lane] = q;
+            vq[2 * lane + 1] = q;
             __syncwarp();
             if (lane > k) {
-              for (int j = k + 1; j < 32; ++j)
-                H[lane * QD_T_HS + j] -= 2.0 * fma(v, qs[j], q * vs[j]);
-              H[lane * QD_T_HS + k] = v;                       // the dead column keeps the reflector
+              const double v2 = -2.0 * v, q2 = -2.0 * q;
+              double* __restrict__ hrow = H + lane * QD_T_HS;
+              for (int j = k + 1; j < 32; ++j) {
+                const double2 o = *reinterpret_cast<const double2*>(vq + 2 * j);     // (v_j, q_j)
+                hrow[j] = fma(v2, o.y, fma(q2, o.x, hrow[j]));
+              }
+              hrow[k] = v;                                     // the dead column keeps the reflector
             }
             if (lane == 0) ee[k] = alpha;
             __syncwarp();
