@@ -38,6 +38,8 @@ struct qd_ctx {
   double* d_nbar = nullptr;       // tunnel path: <n> of every pixel between the two launches
   size_t nbar_cap = 0;
   cudaEvent_t staged = nullptr;   // h_scans may be rewritten once this has fired
+  cudaStream_t s_compute = nullptr, s_copy = nullptr;   // qd_scan_open_host: launches / result copies, overlapped
+  cudaEvent_t chunk_done[16] = {nullptr};
   int up_n_scan = 0;              // descriptors currently resident in d_scans
   int up_max_ny = 0;
   long long up_pixels = 0;        // extent of the output buffers they address
@@ -345,6 +347,9 @@ int qd_create(int device, qd_ctx** out) {
   e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->staged, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking);
+  for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
   if (e != cudaSuccess) {
     fail(nullptr, QD_ERR_CUDA, "device %d init failed: %s", device, cudaGetErrorString(e));
     delete ctx;
@@ -366,6 +371,9 @@ void qd_destroy(qd_ctx* ctx) {
   if (ctx->d_pts) cudaFree(ctx->d_pts);
   if (ctx->d_nbar) cudaFree(ctx->d_nbar);
   if (ctx->staged) cudaEventDestroy(ctx->staged);
+  for (int i = 0; i < 16; ++i) if (ctx->chunk_done[i]) cudaEventDestroy(ctx->chunk_done[i]);
+  if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+  if (ctx->s_copy) cudaStreamDestroy(ctx->s_copy);
   delete ctx;
 }
 
@@ -505,27 +513,51 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   if (rc) return rc;
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
   int max_ny = 0;
-  rc = stage_scans(ctx, n_scan, scans, nullptr, &max_ny);
+  rc = stage_scans(ctx, n_scan, scans, ctx->s_compute, &max_ny);
   if (rc) return rc;
-  long long pixels = 0;
-  for (int i = 0; i < n_scan; ++i) {
-    const long long end = scans[i].pix_offset + (long long)scans[i].nx * scans[i].ny;
-    if (end > pixels) pixels = end;
-  }
+  const long long pixels = ctx->up_pixels;
   const int N = ctx->L.n_dot;
+  const size_t esz = n_elem_size(n_type);
   rc = grow(ctx, &ctx->d_z, &ctx->z_cap, (size_t)pixels * sizeof(float));
   if (rc) return rc;
-  const size_t nbytes = (size_t)pixels * N * n_elem_size(n_type);
-  if (nbytes) {
-    rc = grow(ctx, (unsigned char**)&ctx->d_n, &ctx->n_cap, nbytes);
+  if (esz) {
+    rc = grow(ctx, (unsigned char**)&ctx->d_n, &ctx->n_cap, (size_t)pixels * N * esz);
     if (rc) return rc;
   }
-  rc = launch(ctx, n_scan, ctx->d_scans, max_ny, nullptr, ctx->d_z, ctx->d_n, n_type, flags, nullptr);
-  if (rc) return rc;
-  if (z_out_host)
-    QD_CUDA(ctx, cudaMemcpyAsync(z_out_host, ctx->d_z, (size_t)pixels * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
-  if (nbytes) QD_CUDA(ctx, cudaMemcpyAsync(n_out_host, ctx->d_n, nbytes, cudaMemcpyDeviceToHost, nullptr));
-  QD_CUDA(ctx, cudaStreamSynchronize(nullptr));
+  // Large batches run as a pipeline: the scans are cut into chunks whose output pixel ranges are disjoint and
+  // increasing; chunk c+1 computes on one stream while chunk c's images travel back over PCIe on another.
+  int n_chunk = (n_scan >= 256) ? 8 : 1;
+  std::vector<int> cut(n_chunk + 1);
+  std::vector<long long> lo(n_chunk), hi(n_chunk);
+  for (int c = 0; c <= n_chunk; ++c) cut[c] = (int)((long long)n_scan * c / n_chunk);
+  for (int c = 0; c < n_chunk; ++c) {
+    long long a = -1, b = 0;
+    for (int i = cut[c]; i < cut[c + 1]; ++i) {
+      const long long p0 = scans[i].pix_offset, p1 = p0 + (long long)scans[i].nx * scans[i].ny;
+      if (a < 0 || p0 < a) a = p0;
+      if (p1 > b) b = p1;
+    }
+    lo[c] = a; hi[c] = b;
+    if (c > 0 && lo[c] < hi[c - 1]) { n_chunk = 1; cut[1] = n_scan; lo[0] = 0; hi[0] = pixels; break; }
+  }
+  if (n_chunk == 1) { cut[0] = 0; cut[1] = n_scan; lo[0] = 0; hi[0] = pixels; }
+  const long long all_pixels = ctx->up_pixels;
+  for (int c = 0; c < n_chunk; ++c) {
+    ctx->up_pixels = all_pixels;      // the tunnel scratch is addressed with the scans' own pixel offsets
+    rc = launch(ctx, cut[c + 1] - cut[c], ctx->d_scans + cut[c], max_ny, nullptr, ctx->d_z, ctx->d_n, n_type, flags,
+                ctx->s_compute);
+    if (rc) return rc;
+    QD_CUDA(ctx, cudaEventRecord(ctx->chunk_done[c], ctx->s_compute));
+    QD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->chunk_done[c], 0));
+    if (z_out_host)
+      QD_CUDA(ctx, cudaMemcpyAsync(z_out_host + lo[c], ctx->d_z + lo[c], (size_t)(hi[c] - lo[c]) * sizeof(float),
+                                   cudaMemcpyDeviceToHost, ctx->s_copy));
+    if (esz)
+      QD_CUDA(ctx, cudaMemcpyAsync((char*)n_out_host + (size_t)lo[c] * N * esz, (char*)ctx->d_n + (size_t)lo[c] * N * esz,
+                                   (size_t)(hi[c] - lo[c]) * N * esz, cudaMemcpyDeviceToHost, ctx->s_copy));
+  }
+  QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
+  QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
   return QD_OK;
 }
 

@@ -187,12 +187,20 @@ class Engine:
     def scan_launch(self, z_out, n_out=None, n_type: int = N_NONE, flags: int = 0, stream=None):
         self._check(self._lib.qd_scan_launch(self._ctx, _ptr(z_out), _ptr(n_out), n_type, flags, self._stream(stream)))
 
-    def scan_open_host(self, scans: np.ndarray, n_type: int = N_U8, flags: int = 0, want_z: bool = True):
-        """Synchronous launch returning host arrays ``(z float32 [pixels], n [pixels, N] or None)``."""
+    def scan_open_host(self, scans: np.ndarray, n_type: int = N_U8, flags: int = 0, want_z: bool = True,
+                       z_out: np.ndarray | None = None, n_out: np.ndarray | None = None):
+        """Synchronous launch returning host arrays ``(z float32 [pixels], n [pixels, N] or None)``.
+
+        Large batches are pipelined inside the library (compute of one chunk overlaps the PCIe copy of the previous
+        one); pass pinned ``z_out`` / ``n_out`` (e.g. ``torch.empty(..., pin_memory=True).numpy()``) for full copy speed.
+        """
         assert scans.dtype == SCAN_DTYPE and scans.flags.c_contiguous
         pixels = int((scans["pix_offset"] + scans["nx"].astype(np.int64) * scans["ny"]).max())
-        z = np.empty(pixels, dtype=np.float32) if want_z else None
-        n = np.empty((pixels, self.models.n_dot), dtype=N_DTYPES[n_type]) if n_type != N_NONE else None
+        z = (z_out if z_out is not None else np.empty(pixels, dtype=np.float32)) if want_z else None
+        n = None
+        if n_type != N_NONE:
+            n = n_out if n_out is not None else np.empty((pixels, self.models.n_dot), dtype=N_DTYPES[n_type])
+        assert z is None or (z.dtype == np.float32 and z.size >= pixels and z.flags.c_contiguous)
         self._check(self._lib.qd_scan_open_host(self._ctx, len(scans), _ptr(scans), _ptr(z), _ptr(n), n_type, flags))
         return z, n
 

@@ -27,27 +27,37 @@ CASES = {
     "c4_8dot_latched_full_noise": (8, 1, 32, "default", FLAG_LATCH | FLAG_NOISE | FLAG_RADIAL, dict()),
     "t_3dot_thermal": (3, 2, 32, "default", FLAG_THERMAL, dict(latching=False, noise=False, thermal=True)),
     "t_5dot_thresholded": (5, 1, 32, "thresholded", FLAG_LATCH, dict(noise=False, threshold=0.6)),
+    # Path B (tunnel-coupled, what env.step runs in barrier mode): raw barrier matrices are stored too
+    "b_4dot_tunnel_latched_noise": (4, 1, 24, "tunnel", FLAG_LATCH | FLAG_NOISE, dict()),
+    "b_6dot_tunnel_coupled": (6, 1, 10, "tunnel", 0, dict(latching=False, noise=False)),
 }
 
 
 def main():
     for name, (n_dot, n_env, res, alg, flags, kw) in CASES.items():
         seed = 1000 + sum(map(ord, name))
-        dev = synth.sample_devices(n_env, n_dot, seed=seed)
-        mb = synth.model_batch(dev, algorithm=alg, **kw)
+        if alg == "tunnel":
+            dev = synth.sample_barrier_devices(n_env, n_dot, seed=seed)
+            mb = synth.tunnel_batch(dev, **kw)
+        else:
+            dev = synth.sample_devices(n_env, n_dot, seed=seed)
+            mb = synth.model_batch(dev, algorithm=alg, **kw)
         if flags & FLAG_NOISE:
             mb.params["tele_p01"] = 0.03
             mb.params["tele_p10"] = 0.08
             mb.params["tele_amp"] = 0.01
         scans = synth.env_step_scans(mb, dev, res=res, seed=seed + 1, offset_range=3.0)
+        if alg == "tunnel":
+            scans = scans[:2].copy()
         if n_dot == 2:                      # BASELINE config 1: a single do2d_open window
             scans = scans[:1]
         if flags & FLAG_RADIAL:
             scans["rad_zero_radius"] = 1.0
             scans["rad_alpha"] = 0.02
         z, n, margin = oracle_batch(mb, scans, flags)
+        extra = {k: dev[k] for k in ("Cbd", "Cbg", "Cbs") if k in dev}
         np.savez_compressed(
-            os.path.join(HERE, name + ".npz"),
+            os.path.join(HERE, name + ".npz"), **extra,
             Cdd=dev["Cdd"], Cgd=dev["Cgd"], Cds=dev["Cds"], Cgs=dev["Cgs"], params=mb.params.view(np.uint8),
             scans=scans.view(np.uint8), algorithm=alg, flags=flags, z=z, n=n, margin=margin)
         print(name, z.shape, "n max", n.max(), "min margin", margin.min())

@@ -76,11 +76,18 @@ def load_golden(name):
     from qdsim.engine import ModelBatch
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
     d = np.load(path)
-    mb = ModelBatch.from_capacitances(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"], algorithm=str(d["algorithm"]))
-    mb.params = d["params"].view(PARAMS_DTYPE).copy()
+    params = d["params"].view(PARAMS_DTYPE).copy()
+    if str(d["algorithm"]) == "tunnel":
+        from qdsim.engine import tunnel_model_batch
+        mb = tunnel_model_batch(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"], d["Cbd"], d["Cbg"], d["Cbs"],
+                                params["tc_base"], params["alpha"][:, :d["Cbd"].shape[-1]])
+    else:
+        mb = ModelBatch.from_capacitances(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"], algorithm=str(d["algorithm"]))
+    mb.params = params
     scans = d["scans"].view(SCAN_DTYPE).copy()
     return mb, scans, int(d["flags"]), d["z"], d["n"], d["margin"]
 
 
 GOLDEN_CASES = ["c1_2dot_64x64_noise_free", "c2_4dot_latched_full_noise", "c2b_4dot_flat_pass", "c3_6dot_brute_force",
                 "c4_8dot_latched_full_noise", "t_3dot_thermal", "t_5dot_thresholded"]
+GOLDEN_TUNNEL_CASES = ["b_4dot_tunnel_latched_noise", "b_6dot_tunnel_coupled"]
