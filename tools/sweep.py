@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""BASELINE.json configs 2, 3 and 5 in one run (config 1 is a parity test, config 4 is bench.py's headline):
+
+  config 2: 4-dot, 1024 envs, 64x64, latching + noise           -- Path A (default) and Path B (tunnel-coupled)
+  config 3: 6-dot, 4096 envs (--quick: 256), brute-force search  -- Path A brute_force, max_charge_carriers = 4
+  config 5: N in {2,4,6,8} x res in {32,64,128,256}, Path A default vs the CPU restatement (C port, all cores)
+
+Device-resident timing (descriptors + models in HBM), CUDA events, 3 warm-up launches.  Writes one JSON document.
+    python tools/sweep.py [--quick] > profiles/rNN_sweep.json
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "rl-agent-for-qubit-array-tuning_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_F32, N_U8, Engine, synth  # noqa: E402
+
+FLAGS = FLAG_LATCH | FLAG_NOISE | FLAG_RADIAL
+
+
+def time_gpu(eng, mb, scans, n_type, steps=3, warmup=3):
+    eng.set_models(mb)
+    pixels = int(scans["nx"].astype(np.int64) @ scans["ny"])
+    z = torch.empty(pixels, dtype=torch.float32, device="cuda")
+    n = torch.empty((pixels, mb.n_dot), dtype=torch.uint8 if n_type == N_U8 else torch.float32, device="cuda")
+    st = torch.cuda.current_stream()
+    eng.scan_upload(scans, st)
+    for _ in range(warmup):
+        eng.scan_launch(z, n, n_type, FLAGS, st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(st)
+    for _ in range(steps):
+        eng.scan_launch(z, n, n_type, FLAGS, st)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"pixels": pixels, "ms_per_step": ms, "pixels_per_s": pixels / (ms * 1e-3),
+            "env_steps_per_s": mb.n_env / (ms * 1e-3)}
+
+
+def time_cpu(mb, scans, budget_s=3.0):
+    from oracle import cport
+    cores = os.cpu_count() or 1
+    cal = min(len(scans), 2 * cores)
+    cport.time_scans(mb, scans[:cal], FLAGS, threads=cores)
+    rate, pix, dt = cport.time_scans(mb, scans[:cal], FLAGS, threads=cores)
+    n = int(min(len(scans), max(cal, budget_s * rate / (pix / cal))))
+    pps, pixels, dt = cport.time_scans(mb, scans[:n], FLAGS, threads=cores)
+    return {"pixels_per_s": pps, "cores": cores, "sample_scans": n, "seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    eng = Engine(0)
+    out = {"gpu": torch.cuda.get_device_name(0), "flags": "latching + white/telegraph/radial noise, T=0"}
+
+    # ---- config 2 ----
+    dev = synth.sample_devices(1024, 4, seed=2)
+    mb = synth.model_batch(dev)
+    sc = synth.env_step_scans(mb, dev, res=64, seed=3)
+    c2 = {"path_A_default": time_gpu(eng, mb, sc, N_U8), "cpu_path_A": time_cpu(mb, sc)}
+    devb = synth.sample_barrier_devices(1024, 4, seed=2)
+    mbb = synth.tunnel_batch(devb)
+    scb = synth.env_step_scans(mbb, devb, res=64, seed=3)
+    c2["path_B_tunnel"] = time_gpu(eng, mbb, scb, N_F32, steps=2, warmup=1)
+    out["config2_4dot_1024env_64x64"] = c2
+
+    # ---- config 3 ----
+    n_env3 = 256 if args.quick else 4096
+    dev = synth.sample_devices(n_env3, 6, seed=4)
+    mb = synth.model_batch(dev, algorithm="brute_force", max_charge_carriers=4)
+    sc = synth.env_step_scans(mb, dev, res=64, seed=5)
+    c3 = {"path_A_brute_force": time_gpu(eng, mb, sc, N_U8, steps=2, warmup=1)}
+    c3["cpu_brute_force"] = time_cpu(mb, sc[:64], budget_s=3.0)
+    mbd = synth.model_batch(dev, algorithm="default")
+    c3["path_A_default_same_devices"] = time_gpu(eng, mbd, sc, N_U8)
+    out[f"config3_6dot_{n_env3}env_64x64"] = c3
+
+    # ---- config 5 ----
+    sweep = []
+    for n_dot in (2, 4, 6, 8):
+        for res in (32, 64, 128, 256):
+            n_env = max(16, int((2e8 if not args.quick else 2e7) / ((n_dot - 1) * res * res)))
+            dev = synth.sample_devices(n_env, n_dot, seed=6)
+            mb = synth.model_batch(dev)
+            sc = synth.env_step_scans(mb, dev, res=res, seed=7)
+            g = time_gpu(eng, mb, sc, N_U8)
+            c = time_cpu(mb, sc, budget_s=1.5)
+            sweep.append({"n_dot": n_dot, "res": res, "n_env": n_env, "gpu_pixels_per_s": g["pixels_per_s"],
+                          "gpu_ms": g["ms_per_step"], "cpu_pixels_per_s": c["pixels_per_s"], "cpu_cores": c["cores"],
+                          "ratio": g["pixels_per_s"] / c["pixels_per_s"]})
+            print(sweep[-1], file=sys.stderr)
+    out["config5_sweep_path_A_default"] = sweep
+    out["launches"] = eng.launch_count
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
