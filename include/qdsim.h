@@ -152,6 +152,15 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
 int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const double* v, float* z_out_host,
                         void* n_out_host, int n_type, unsigned flags);
 
+/* Percentile normalisation of the observation images, per env (K8; replaces QuantumDeviceEnv._normalise_obs,
+ * src/qadapt/environment/env.py:471-509): for each of n_env consecutive blocks of per_env floats,
+ *   p_low, p_high = np.percentile(block, q_low_pct), np.percentile(block, q_high_pct)   (numpy 'linear' method)
+ *   out = clip((block - p_low) / (p_high - p_low), 0, 1)   or zeros when p_high <= p_low
+ * z and out are DEVICE pointers (out may alias z); stats (DEVICE, [n_env, 2] doubles: p_low, p_high) may be NULL.
+ * Asynchronous on `stream`. */
+int qd_normalise_obs(qd_ctx* ctx, const float* z, float* out, int64_t per_env, int n_env, double q_low_pct,
+                     double q_high_pct, double* stats, void* stream);
+
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t qd_launch_count(const qd_ctx* ctx);
 

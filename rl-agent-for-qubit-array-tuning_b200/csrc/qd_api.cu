@@ -10,6 +10,7 @@
 
 #include "qd_kernels.cuh"
 #include "qd_tunnel.cuh"
+#include "qd_normalise.cuh"
 
 static_assert(sizeof(qd_scan) == 480, "qd_scan must be 480 bytes (multiple of 16 for the TMA bulk copy)");
 static_assert(sizeof(qd_scan) % 16 == 0, "qd_scan size");
@@ -593,6 +594,21 @@ int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const 
     QD_CUDA(ctx, cudaMemcpyAsync(z_out_host, ctx->d_z, (size_t)pixels * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
   if (nbytes) QD_CUDA(ctx, cudaMemcpyAsync(n_out_host, ctx->d_n, nbytes, cudaMemcpyDeviceToHost, nullptr));
   QD_CUDA(ctx, cudaStreamSynchronize(nullptr));
+  return QD_OK;
+}
+
+int qd_normalise_obs(qd_ctx* ctx, const float* z, float* out, int64_t per_env, int n_env, double q_low_pct,
+                     double q_high_pct, double* stats, void* stream) {
+  if (!ctx) return fail(nullptr, QD_ERR_INVALID, "ctx is NULL");
+  if (!z || !out) return fail(ctx, QD_ERR_INVALID, "NULL image pointer");
+  if (per_env <= 0 || n_env <= 0) return fail(ctx, QD_ERR_INVALID, "per_env and n_env must be positive");
+  if (!(q_low_pct >= 0.0 && q_low_pct <= q_high_pct && q_high_pct <= 100.0))
+    return fail(ctx, QD_ERR_INVALID, "percentiles must satisfy 0 <= low <= high <= 100");
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  qd::qd_normalise_kernel<<<n_env, 512, 0, (cudaStream_t)stream>>>(z, out, per_env, n_env, q_low_pct / 100.0,
+                                                                     q_high_pct / 100.0, stats);
+  QD_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
   return QD_OK;
 }
 

@@ -1,0 +1,91 @@
+// qd_normalise.cuh -- K8: per-env percentile normalisation of the observation images (first "next" row of SURVEY 8f).
+// Replaces QuantumDeviceEnv._normalise_obs (src/qadapt/environment/env.py:471-509):
+//     p_low, p_high = np.percentile(image, 0.5), np.percentile(image, 99.5)      # over ALL channels of the env
+//     image = clip((image - p_low) / (p_high - p_low), 0, 1).astype(float32)      # zeros if p_high <= p_low
+// One CTA per env.  The four order statistics the two interpolated percentiles need (ranks k, k+1 at both ends) are
+// found EXACTLY by a 4-pass 8-bit radix select over the monotone uint32 image of the fp32 values (shared-memory
+// histograms, four ranks tracked at once), then one more pass normalises in fp64 and writes fp32.  HBM-bound:
+// 5 reads + 1 write of 4 B per pixel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qd {
+
+__device__ __forceinline__ uint32_t f32_key(float x) {
+  const uint32_t u = __float_as_uint(x);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // order-preserving map float -> uint32
+}
+__device__ __forceinline__ float key_f32(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// numpy's _lerp (lib/_function_base_impl.py): a + (b-a) t, or b - (b-a)(1-t) when t >= 0.5
+__device__ __forceinline__ double np_lerp(double a, double b, double t) {
+  const double d = b - a;
+  return (t >= 0.5) ? b - d * (1.0 - t) : a + d * t;
+}
+
+__global__ void __launch_bounds__(512) qd_normalise_kernel(const float* __restrict__ z, float* __restrict__ out,
+                                                           long long per_env, int n_env, double q_lo, double q_hi,
+                                                           double* __restrict__ stats) {
+  __shared__ unsigned hist[4][256];
+  __shared__ uint32_t prefix[4];
+  __shared__ long long rank[4];
+  const int env = blockIdx.x;
+  if (env >= n_env) return;
+  const float* __restrict__ src = z + (size_t)env * per_env;
+  // numpy 'linear' percentile: virtual index (n-1) q, neighbours floor / floor+1 (clamped), weight = fractional part
+  const double vi_lo = (double)(per_env - 1) * q_lo, vi_hi = (double)(per_env - 1) * q_hi;
+  const long long k_lo = (long long)floor(vi_lo), k_hi = (long long)floor(vi_hi);
+  if (threadIdx.x == 0) {
+    rank[0] = k_lo; rank[1] = min(k_lo + 1, per_env - 1);
+    rank[2] = k_hi; rank[3] = min(k_hi + 1, per_env - 1);
+    prefix[0] = prefix[1] = prefix[2] = prefix[3] = 0u;
+  }
+  __syncthreads();
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) (&hist[0][0])[i] = 0u;
+    __syncthreads();
+    const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
+    const uint32_t p0 = prefix[0], p1 = prefix[1], p2 = prefix[2], p3 = prefix[3];
+    for (long long i = threadIdx.x; i < per_env; i += blockDim.x) {
+      const uint32_t k = f32_key(src[i]);
+      const uint32_t b = (k >> shift) & 0xffu, top = k & hi_mask;
+      if (top == p0) atomicAdd(&hist[0][b], 1u);
+      if (top == p1) atomicAdd(&hist[1][b], 1u);
+      if (top == p2) atomicAdd(&hist[2][b], 1u);
+      if (top == p3) atomicAdd(&hist[3][b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+      const int t = threadIdx.x;
+      long long r = rank[t];
+      int b = 0;
+      for (; b < 255; ++b) {
+        const unsigned c = hist[t][b];
+        if (r < (long long)c) break;
+        r -= c;
+      }
+      rank[t] = r;
+      prefix[t] |= (uint32_t)b << shift;
+    }
+    __syncthreads();
+  }
+  const double a_lo = (double)key_f32(prefix[0]), b_lo = (double)key_f32(prefix[1]);
+  const double a_hi = (double)key_f32(prefix[2]), b_hi = (double)key_f32(prefix[3]);
+  const double p_low = np_lerp(a_lo, b_lo, vi_lo - (double)k_lo);
+  const double p_high = np_lerp(a_hi, b_hi, vi_hi - (double)k_hi);
+  if (stats && threadIdx.x == 0) { stats[2 * env] = p_low; stats[2 * env + 1] = p_high; }
+  const bool ok = p_high > p_low;
+  const double span = p_high - p_low;
+  float* __restrict__ dst = out + (size_t)env * per_env;
+  for (long long i = threadIdx.x; i < per_env; i += blockDim.x) {
+    double v = ok ? ((double)src[i] - p_low) / span : 0.0;
+    v = fmin(fmax(v, 0.0), 1.0);
+    dst[i] = (float)v;
+  }
+}
+
+}  // namespace qd

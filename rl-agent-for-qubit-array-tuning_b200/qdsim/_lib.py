@@ -59,7 +59,7 @@ def lib_path() -> str:
 
 
 EXPORTS = ("qd_abi_version", "qd_create", "qd_destroy", "qd_last_error", "qd_set_models", "qd_scan_open",
-           "qd_scan_upload", "qd_scan_launch", "qd_scan_open_host", "qd_points_open_host", "qd_launch_count", "qd_measure_fp64_peak",
+           "qd_scan_upload", "qd_scan_launch", "qd_scan_open_host", "qd_normalise_obs", "qd_points_open_host", "qd_launch_count", "qd_measure_fp64_peak",
            "qd_measure_fp32_peak")
 
 _lib = None
@@ -95,6 +95,8 @@ def load() -> C.CDLL:
     lib.qd_scan_open_host.restype = C.c_int
     lib.qd_points_open_host.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp, vp, C.c_int, C.c_uint]
     lib.qd_points_open_host.restype = C.c_int
+    lib.qd_normalise_obs.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_double, C.c_double, vp, vp]
+    lib.qd_normalise_obs.restype = C.c_int
     lib.qd_launch_count.argtypes = [vp]
     lib.qd_launch_count.restype = C.c_int64
     lib.qd_measure_fp64_peak.argtypes = [vp, C.c_int, dp]

@@ -218,6 +218,17 @@ class Engine:
                                                   flags))
         return z, n
 
+    def normalise_obs(self, z, out=None, per_env: int | None = None, n_env: int | None = None, q_low: float = 0.5,
+                      q_high: float = 99.5, stats=None, stream=None):
+        """Per-env percentile normalisation of DEVICE images (``QuantumDeviceEnv._normalise_obs``, env.py:471-509):
+        ``z`` holds ``n_env`` consecutive blocks of ``per_env`` float32 (all channels of one env); in place by default."""
+        out = z if out is None else out
+        n_env = self.models.n_env if n_env is None else n_env
+        per_env = z.numel() // n_env if per_env is None else per_env
+        self._check(self._lib.qd_normalise_obs(self._ctx, _ptr(z), _ptr(out), per_env, n_env, q_low, q_high, _ptr(stats),
+                                               self._stream(stream)))
+        return out
+
     # -- introspection ---------------------------------------------------------------------------------------
     @property
     def launch_count(self) -> int:

@@ -1,0 +1,94 @@
+"""Batched observation stage (first 'next' row): descriptor synthesis on the CPU, percentile
+normalisation and the whole observe() call on the GPU."""
+import numpy as np
+import pytest
+
+from oracle import composer
+
+
+def _state(n_env, n_dot, seed):
+    from qdsim import synth
+    rng = np.random.default_rng(seed)
+    dev = synth.sample_devices(n_env, n_dot, seed=seed)
+    mb = synth.model_batch(dev)
+    gv = rng.uniform(-2, 4, (n_env, n_dot))
+    vgm = -np.eye(n_dot + 1) + rng.normal(0, 0.05, (n_env, n_dot + 1, n_dot + 1))
+    origin = rng.normal(0, 0.1, (n_env, n_dot + 1))
+    sv = rng.uniform(0.3, 0.7, n_env)
+    return dev, mb, gv, vgm, origin, sv
+
+
+def test_obs_scans_match_the_composer_env_by_env():
+    from qdsim import obs
+    dev, mb, gv, vgm, origin, sv = _state(5, 4, 1)
+    scans = obs.obs_scans(mb, gv, sv, vgm, origin, -1.7, 1.7, 16, peak_width=dev["peak_width"], seeds=np.arange(15))
+    assert len(scans) == 15
+    for e in range(5):
+        for c in range(3):
+            rec = scans[e * 3 + c]
+            want = composer.do2d_virtual_coupled(5, c + 1, gv[e, c] - 1.7, gv[e, c] + 1.7, 16, c + 2, gv[e, c + 1] - 1.7,
+                                                 gv[e, c + 1] + 1.7, 16, np.append(gv[e], sv[e]), vgm[e], origin[e])
+            got = composer.affine_grid(rec["v0"][:5], rec["dx"][:5], rec["dy"][:5], 16, 16)
+            assert np.allclose(got, want, atol=1e-12)
+            assert rec["env_id"] == e and rec["pix_offset"] == (e * 3 + c) * 256
+    phys = obs.obs_scans(mb, gv, 0.0, None, None, -1.0, 1.0, 8, virtual=False, seeds=np.arange(15))
+    want = composer.do2d(5, 2, gv[3, 1] - 1, gv[3, 1] + 1, 8, 3, gv[3, 2] - 1, gv[3, 2] + 1, 8)
+    rec = phys[3 * 3 + 1]
+    assert np.allclose(composer.affine_grid(rec["v0"][:5], rec["dx"][:5], rec["dy"][:5], 8, 8), want, atol=1e-12)
+
+
+def test_obs_scans_radial_and_peak_width_rules():
+    from qdsim import obs
+    dev, mb, gv, vgm, origin, sv = _state(4, 3, 2)
+    gt = gv + np.array([[0.5, 0.2, 0.1], [35.0, 0.0, 0.0], [0.0, 0.0, -50.0], [1.0, 1.0, 1.0]])
+    radial = dict(zero_radius=np.full(4, 25.0), ramp_distance=np.full(4, 32.0), full_noise_distance=np.full(4, 33.0),
+                  max_amplitude=0.05)
+    s = obs.obs_scans(mb, gv, sv, vgm, origin, -1.5, 1.5, 32, gate_ground_truth=gt, radial=radial,
+                      peak_width=0.3, peak_width_alpha=0.01, seeds=np.arange(8))
+    assert list(s["rad_mode"]) == [1, 1, 2, 1, 1, 2, 1, 1]          # a pair is replaced iff either dot is > 33 V away
+    assert np.allclose(s["rad_alpha"], 0.05 / 32.0) and np.allclose(s["rad_x0"][0], gv[0, 0] - 1.5 - gt[0, 0])
+    want_pw = np.clip(0.3 - np.abs(0.01 * (abs(gv[0, 0]) + abs(gv[0, 1])) / 2), 0, 1)
+    assert np.isclose(s["peak_width"][0], want_pw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_env,n_env", [(3 * 32 * 32, 7), (1000, 3), (7 * 64 * 64, 4), (2, 2)])
+def test_percentile_normalisation_is_bit_exact_vs_numpy(engine, per_env, n_env):
+    import torch
+    rng = np.random.default_rng(per_env)
+    z = rng.normal(0.6, 0.3, (n_env, per_env)).astype(np.float32)
+    z[0, : per_env // 2] = z[0, 0]                                   # heavy ties
+    if n_env > 2:
+        z[2] = 0.25                                                  # constant image -> zeros
+    z_dev = torch.from_numpy(z).cuda()
+    stats = torch.empty((n_env, 2), dtype=torch.float64, device="cuda")
+    out = engine.normalise_obs(z_dev.clone(), per_env=per_env, n_env=n_env, stats=stats)
+    torch.cuda.synchronize()
+    for e in range(n_env):
+        img = z[e].astype(np.float64)
+        p_low, p_high = np.percentile(img, 0.5), np.percentile(img, 99.5)
+        want = np.clip((img - p_low) / (p_high - p_low), 0, 1) if p_high > p_low else np.zeros_like(img)
+        assert stats[e, 0].item() == p_low and stats[e, 1].item() == p_high
+        assert np.array_equal(out[e].cpu().numpy(), want.astype(np.float32))
+
+
+@pytest.mark.gpu
+def test_observe_batch_end_to_end(engine):
+    """obs_scans -> scan kernel -> normalisation, against the oracle + np.percentile env by env."""
+    import torch
+    from qdsim import FLAG_LATCH, N_NONE, obs
+    from util import oracle_batch
+    dev, mb, gv, vgm, origin, sv = _state(3, 4, 3)
+    engine.set_models(mb)
+    scans = obs.obs_scans(mb, gv, sv, vgm, origin, -1.8, 1.8, 32, peak_width=dev["peak_width"], seeds=np.arange(9) + 5)
+    z_dev = torch.empty(9 * 32 * 32, dtype=torch.float32, device="cuda")
+    img = obs.observe(engine, scans, z_dev, flags=FLAG_LATCH)
+    torch.cuda.synchronize()
+    assert img.shape == (3, 3, 32, 32)
+    z_ref, _, _ = oracle_batch(mb, scans, FLAG_LATCH)
+    z_ref = z_ref.reshape(3, 3, 32, 32)
+    for e in range(3):
+        p_low, p_high = np.percentile(z_ref[e], 0.5), np.percentile(z_ref[e], 99.5)
+        want = np.clip((z_ref[e] - p_low) / (p_high - p_low), 0, 1)
+        np.testing.assert_allclose(img[e].cpu().numpy(), want, rtol=0, atol=5e-6)
+    assert img.min().item() == 0.0 and img.max().item() == 1.0
