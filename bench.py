@@ -291,7 +291,6 @@ def main():
         ev[k + 1].record(stream)
     barrier()
     launches = eng.launch_count - launches0
-    clocks = sampler.stop() if rank == 0 else None
     kernel_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     ms_per_step = total_ms / args.steps
@@ -322,6 +321,7 @@ def main():
         e2e_step(k)
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions
     barrier()
     e2e_ms = max_over_ranks(wall_ms) / args.steps
     e2e_value = world * pixels / (e2e_ms * 1e-3)
@@ -346,7 +346,10 @@ def main():
             "flop_per_pixel": f_exec, "flop_per_pixel_reference_formulation": f_ref,
             "pipe_slot_frac": pix_s_kernel * fp64_pipe_ops_factored(N) * 2e-12 / fp64_peak,
             "kernel_ms": k_ms, "fp32_peak": fp32_peak,
-            "traffic": None,
+            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
+            # (profiles/r01_ncu_summary.md: 687 MB per launch of 58.7 Mpixel = 11.7 B/pixel), scaled to this launch
+            "traffic": 11.7 * pixels if (N == 8 and args.path == "A") else None,
+            "traffic_source": "ncu --set full capture at 2048 envs (profiles/), scaled per pixel",
             "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": hbm_achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
                     "algorithmic_bytes_per_pixel": bytes_per_pixel},

@@ -76,6 +76,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
 // order prior generic-proxy accesses to shared memory before subsequent async-proxy (TMA) writes
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// min by one DSETP.LT + select pair (the C ternary is pattern-matched into DSETP.MIN plus NaN fix-ups: twice the work)
+__device__ __forceinline__ double min_lt(double e, double m) {
+  double r;
+  asm("{\n .reg .pred p;\n setp.lt.f64 p, %1, %2;\n selp.f64 %0, %1, %2, p;\n}" : "=d"(r) : "d"(e), "d"(m));
+  return r;
+}
+
 // MUFU.RCP, ~1 ulp: the Lorentzian sum tolerates it (error budget of the sensor signal)
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;

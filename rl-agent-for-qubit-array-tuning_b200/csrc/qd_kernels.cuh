@@ -306,13 +306,13 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
         const double2 qq = *reinterpret_cast<const double2*>(q + b);
         const double e0 = llo[b] + qq.x;
         const double e1 = llo[b + 1] + qq.y;
-        m0 = (e0 < m0) ? e0 : m0;
-        m1 = (e1 < m1) ? e1 : m1;
+        m0 = min_lt(e0, m0);
+        m1 = min_lt(e1, m1);
       }
     } else {
       m0 = llo[0] + q[0];
     }
-    const double m = (m1 < m0) ? m1 : m0;
+    const double m = min_lt(m1, m0);
     const double e = m + lh;
     if (e < best) { best = e; best_m = m; best_h = H; }
   }
