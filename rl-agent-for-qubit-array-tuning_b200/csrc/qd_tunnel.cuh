@@ -77,12 +77,15 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
   constexpr int B = N - 1;
 
   extern __shared__ __align__(128) unsigned char qd_smem[];
+  __shared__ double sq_tab[258];                   // sqrt(k), k = 0..257: hopping amplitudes sqrt(n_from (n_to + 1))
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const qd_layout& L = a.L;
   const int NV = L.n_volt, G = L.n_gate;
   const bool barriers = NV > G;
+  for (int k = threadIdx.x; k < 258; k += blockDim.x) sq_tab[k] = sqrt((double)k);
+  __syncthreads();
 
   unsigned char* slot = qd_smem + (size_t)warp * a.slot_bytes;
   double* rec = reinterpret_cast<double*>(slot);
@@ -347,33 +350,21 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               Fm = fma(zz[i], s, Fm);
             }
           }
-          // hopping amplitudes out of this lane's state, one square root per (bond, direction)
-          double amp_f[B], amp_b[B];
-#pragma unroll
-          for (int d = 0; d < B; ++d) {
-            amp_f[d] = -ts[d] * sqrt(st[d] * (st[d + 1] + 1.0));        // d -> d+1
-            amp_b[d] = -ts[d] * sqrt(st[d + 1] * (st[d] + 1.0));        // d+1 -> d
-          }
+          // Row `lane` of H.  Two states are connected by a hop iff they differ in exactly two ADJACENT dots, by
+          // (-1, +1) or (+1, -1): test on the XOR of the packed states first (cheap reject), then compare the byte pair.
 #pragma unroll 1
           for (int j = 0; j < 32; ++j) {
             const uint64_t kj = shfl_u64(key, j);
             double val = (j == lane) ? Fm : 0.0;
-            // per-byte difference kj - key (SWAR, no carries across bytes)
             const uint64_t Hm = 0x8080808080808080ULL;
-            const uint64_t d = ((kj | Hm) - (key & ~Hm)) ^ ((kj ^ ~key) & Hm);
-            const uint64_t nz = (((d & ~Hm) + ~Hm) | d) & Hm;
-            if (__popcll(nz) == 2) {
+            const uint64_t x = kj ^ key;
+            const uint64_t nz = (((x & ~Hm) + ~Hm) | x) & Hm;
+            if (__popcll(nz) == 2 && (nz & (nz >> 8))) {
               const int p0 = (__ffsll((long long)nz) - 1) >> 3;
-              const int p1 = (63 - __clzll((long long)nz)) >> 3;
-              if (p1 == p0 + 1) {
-                const unsigned b0 = (unsigned)(d >> (8 * p0)) & 0xffu, b1 = (unsigned)(d >> (8 * p1)) & 0xffu;
-                const bool fwd = b0 == 0xffu && b1 == 0x01u, bwd = b0 == 0x01u && b1 == 0xffu;
-                if (fwd || bwd) {
-#pragma unroll
-                  for (int dd_ = 0; dd_ < B; ++dd_)
-                    if (p0 == dd_) val = fwd ? amp_f[dd_] : amp_b[dd_];
-                }
-              }
+              const unsigned pa = (unsigned)(key >> (8 * p0)) & 0xffffu, pb = (unsigned)(kj >> (8 * p0)) & 0xffffu;
+              const unsigned a0 = pa & 0xffu, a1 = pa >> 8;
+              if (pb == pa + 0xffu) val = -ts[p0] * (sq_tab[a0] * sq_tab[a1 + 1]);        // p0 -> p0+1
+              else if (pb + 0xffu == pa) val = -ts[p0] * (sq_tab[a1] * sq_tab[a0 + 1]);   // p0+1 -> p0
             }
             H[lane * QD_T_HS + j] = val;
           }
@@ -439,13 +430,21 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           __syncwarp();
           for (int round = 0; round < 7; ++round) {
             const double x = fma((double)(lane + 1) * (1.0 / 33.0), hi - lo, lo);
-            double q = dd[0] - x;
-            if (q == 0.0) q = 1e-300;
-            int cnt = q < 0.0;
+            // Sturm count in product form p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1} (no division); the count is the
+            // number of sign changes, an exact zero inheriting the sign of its predecessor; rescaled against overflow.
+            double pp = 1.0, pc = dd[0] - x;
+            bool neg = pc < 0.0;
+            int cnt = neg;
             for (int i = 1; i < 32; ++i) {
-              q = (dd[i] - x) - e2[i - 1] * __drcp_rn(q);
-              if (q == 0.0) q = 1e-300;
-              cnt += q < 0.0;
+              double pn = fma(dd[i] - x, pc, -e2[i - 1] * pp);
+              const bool nneg = (pn < 0.0) || (pn == 0.0 && neg);
+              cnt += nneg != neg;
+              neg = nneg;
+              const double an = fabs(pn);
+              if (an > 1e100) { pn *= 1e-100; pc *= 1e-100; }
+              else if (an < 1e-100 && an > 0.0) { pn *= 1e100; pc *= 1e100; }
+              pp = pc;
+              pc = pn;
             }
             const unsigned mm = __ballot_sync(0xffffffffu, cnt >= 1);
             const int j = mm ? __ffs(mm) - 1 : 32;
@@ -470,7 +469,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           }
           yy[lane] = 1.0 + (double)lane * (1.0 / 64.0);
           __syncwarp();
-          for (int it = 0; it < 5; ++it) {
+          for (int it = 0; it < 3; ++it) {
             if (lane == 0) {
               double zprev = yy[0];
               for (int i = 1; i < 32; ++i) { zprev = yy[i] - ll[i - 1] * zprev; yy[i] = zprev; }
