@@ -19,7 +19,7 @@ ALG = {"default": 0, "thresholded": 1, "brute_force": 2}
 
 def build(force: bool = False) -> str:
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(_SRC):
-        subprocess.check_call(["gcc", "-O3", "-march=native", "-fopenmp", "-fPIC", "-shared", "-o", _LIB, _SRC, "-lm"])
+        subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-o", _LIB, _SRC, "-lm"])
     return _LIB
 
 

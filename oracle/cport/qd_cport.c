@@ -9,7 +9,7 @@
  * sequential loops along the scan.  Parallelism = OpenMP over scans / rows, like the upstream Rust core's rayon loop
  * over voltage points.
  *
- * Build: gcc -O3 -march=native -fopenmp -fPIC -shared -o libqd_cport.so qd_cport.c -lm
+ * Build: gcc -O3 -march=x86-64-v3 -fopenmp -fPIC -shared -o libqd_cport.so qd_cport.c -lm
  */
 #include <math.h>
 #include <stdint.h>

@@ -126,45 +126,6 @@ kernel_fn pick_kernel(const qd_layout& L) {
   return nullptr;
 }
 
-// Tunnel path: Schur complement of the high block and the quadratic tables of the two halves of the candidate digits.
-bool pack_tunnel_tables(const qd_layout& L, double* r) {
-  const int N = L.n_dot, nlo = N < 4 ? N : 4, nhi = N - nlo;
-  const double* C = r + L.o_cinv;
-  // Cll^-1 by Gauss-Jordan (SPD, tiny)
-  double a[4][8];
-  for (int i = 0; i < nlo; ++i)
-    for (int j = 0; j < nlo; ++j) { a[i][j] = C[(nhi + i) * N + nhi + j]; a[i][nlo + j] = (i == j) ? 1.0 : 0.0; }
-  for (int k = 0; k < nlo; ++k) {
-    const double piv = a[k][k];
-    if (!(piv > 0.0)) return false;
-    for (int j = 0; j < 2 * nlo; ++j) a[k][j] /= piv;
-    for (int i = 0; i < nlo; ++i) {
-      if (i == k) continue;
-      const double f = a[i][k];
-      for (int j = 0; j < 2 * nlo; ++j) a[i][j] -= f * a[k][j];
-    }
-  }
-  for (int i = 0; i < nhi; ++i)
-    for (int j = 0; j < nhi; ++j) {
-      double s = C[i * N + j];
-      for (int p = 0; p < nlo; ++p)
-        for (int q = 0; q < nlo; ++q) s -= C[i * N + nhi + p] * a[p][nlo + q] * C[(nhi + q) * N + j];
-      r[L.o_schur + i * nhi + j] = s;
-    }
-  for (int half = 0; half < 2; ++half) {
-    const int nd = half ? nlo : nhi, off = half ? nhi : 0, base = half ? L.o_qll : L.o_qhh;
-    for (int idx = 0; idx < (1 << (2 * nd)); ++idx) {
-      double x[4];
-      for (int j = 0; j < nd; ++j) x[j] = (double)((idx >> (2 * (nd - 1 - j))) & 3) - 1.0;
-      double s = 0.0;
-      for (int i = 0; i < nd; ++i)
-        for (int j = 0; j < nd; ++j) s += x[i] * C[(off + i) * N + off + j] * x[j];
-      r[base + idx] = s;
-    }
-  }
-  return true;
-}
-
 int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) {
   if (!ctx) return fail(nullptr, QD_ERR_INVALID, "ctx is NULL");
   if (!ctx->have_models) return fail(ctx, QD_ERR_STATE, "qd_set_models has not been called");
@@ -457,7 +418,6 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
     }
     if (alg == QD_ALG_TUNNEL) {
       if (cbg && NV > G) memcpy(r + L.o_cbg, cbg + (size_t)e * (NV - G) * G, sizeof(double) * (NV - G) * G);
-      if (!pack_tunnel_tables(L, r)) return fail(ctx, QD_ERR_INVALID, "env %d: cdd_inv block is singular", e);
     }
   }
   QD_CUDA(ctx, cudaDeviceSynchronize());   // nothing in flight may still read the old records

@@ -37,9 +37,7 @@ struct qd_layout {
   int32_t o_sneg;    // [8]        2 * sum_{k != j} min(Cinv_jk, 0)
   int32_t o_q;       // [2^N]      Q[delta] = delta^T cdd_inv delta, delta in {0,1}^N, dot 0 = most significant bit
   int32_t o_cbg;     // [B*G]      (tunnel) raw positive barrier-gate matrix
-  int32_t o_schur;   // [NHI*NHI]  (tunnel) Schur complement Chh - Chl Cll^-1 Clh: lower bound of a block of candidates
-  int32_t o_qhh;     // [4^NHI]    (tunnel) x^T Chh x over x in {-1,0,1,2}^NHI (first dots), base-4 index, first dot slowest
-  int32_t o_qll;     // [4^NLO]    (tunnel) y^T Cll y over y in {-1,0,1,2}^NLO (last dots)
+  int32_t o_schur, o_qhh, o_qll;   // unused (kept for ABI stability of the struct): tunnel tables live in the kernel
   int32_t rec_doubles;  // total, multiple of 2 (16 bytes)
 };
 
@@ -68,12 +66,7 @@ static inline qd_layout qd_make_layout(int n_dot, int n_volt, int n_gate, int al
   L.o_schur = o;
   L.o_qhh = o;
   L.o_qll = o;
-  if (algorithm == QD_ALG_TUNNEL) {
-    const int nlo = n_dot < 4 ? n_dot : 4, nhi = n_dot - nlo;
-    L.o_schur = o; o += nhi * nhi;
-    L.o_qhh = o;   o += 1 << (2 * nhi);
-    L.o_qll = o;   o += 1 << (2 * nlo);
-  }
+  // (the tunnel path's block tables depend on a per-item permutation of the dots and are built inside the kernel)
   L.rec_doubles = (o + 1) & ~1;
   return L;
 }

@@ -23,7 +23,8 @@
 namespace qd {
 
 constexpr int QD_T_HS = 33;                       // row stride of H in shared memory (bank-conflict free)
-constexpr int QD_T_WORK = 32 * QD_T_HS + 9 * 32 + 64;   // H, dd, ee, e2, qi, ll, yy, vs, qs, spare | small vectors
+constexpr int QD_T_TAB = 64 + 16 + 256 + 256 + 16;      // per-item: permuted Cinv, Schur block, Qhh, Qll, perm / inverse perm
+constexpr int QD_T_WORK = 32 * QD_T_HS + 9 * 32 + 64 + QD_T_TAB;   // H, dd, ee, e2, qi, ll, yy, vq | small vectors | tables
 
 __host__ __device__ inline int qd_tunnel_slot_bytes(const qd_layout& L) {
   int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_T_WORK * 8 + 16;
@@ -108,6 +109,11 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
   double* hs = sv + 40;
   double* ts = sv + 48;
   double* nb = sv + 56;
+  double* Cp = sv + 64;          // Cinv with rows / columns permuted so that the stiffest dots come first
+  double* Sp = Cp + 64;          // Schur complement of the permuted high block
+  double* Qh = Sp + 16;          // x^T Cp_hh x over the high digit combinations
+  double* Ql = Qh + 256;         // y^T Cp_ll y over the low digit combinations
+  int* pm = reinterpret_cast<int*>(Ql + 256);   // pm[j]: dot at permuted position j;  pm[8 + d]: position of dot d
   uint64_t* bar = reinterpret_cast<uint64_t*>(wk + QD_T_WORK);
 
   const double* __restrict__ C = rec + L.o_cinv;
@@ -143,6 +149,78 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
     const double* par = rec + L.o_par;
     const bool replace = (a.flags & QD_FLAG_RADIAL) && sc->rad_mode == 2;
     const long long pix0 = sc->pix_offset;
+
+    // ---- per-item split of the dots into a high and a low half ----
+    // Any split is exact; its only job is to make the block bound bite.  Dots that are empty and far below their
+    // first charge transition (very negative potential) have no cheap excitation: putting them in the HIGH half makes
+    // every block that moves them cost far more than the 32nd-best energy, so it is never visited.  The order is
+    // taken from the potentials at the item's first pixel; the tables of the two halves are rebuilt for it here.
+    if (!replace) {
+      const long long pf = p_begin;
+      const int fy = (int)(pf / nx), fx = (int)(pf - (long long)fy * nx);
+      if (lane < NV)
+        vv[lane] = (a.points == nullptr) ? fma((double)fy, sc->dy[lane], fma((double)fx, sc->dx[lane], sc->v0[lane]))
+                                         : a.points[(size_t)pf * NV + lane];
+      __syncwarp();
+      if (lane < N) {
+        double acc = 0.0;
+        for (int k = 0; k < NV; ++k) acc = fma(rec[L.o_a + lane * NV + k], vv[k], acc);
+        gs[lane] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        int ord[N];
+        for (int j = 0; j < N; ++j) ord[j] = j;
+        for (int i = 1; i < N; ++i) {                      // insertion sort, ascending potential (most negative first)
+          const int o = ord[i];
+          int j = i - 1;
+          while (j >= 0 && gs[ord[j]] > gs[o]) { ord[j + 1] = ord[j]; --j; }
+          ord[j + 1] = o;
+        }
+        for (int j = 0; j < N; ++j) { pm[j] = ord[j]; pm[8 + ord[j]] = j; }
+      }
+      __syncwarp();
+      for (int e = lane; e < N * N; e += 32) Cp[e] = C[pm[e / N] * N + pm[e % N]];
+      __syncwarp();
+      if (lane == 0) {
+        // Sp = Chh - Chl Cll^-1 Clh  (Gauss-Jordan on the low block, <= 4 x 4)
+        double m[4][8];
+        for (int i = 0; i < NLO; ++i)
+          for (int j = 0; j < NLO; ++j) { m[i][j] = Cp[(NHI + i) * N + NHI + j]; m[i][NLO + j] = (i == j) ? 1.0 : 0.0; }
+        for (int k = 0; k < NLO; ++k) {
+          const double inv = 1.0 / m[k][k];
+          for (int j = 0; j < 2 * NLO; ++j) m[k][j] *= inv;
+          for (int i = 0; i < NLO; ++i) {
+            if (i == k) continue;
+            const double fac = m[i][k];
+            for (int j = 0; j < 2 * NLO; ++j) m[i][j] -= fac * m[k][j];
+          }
+        }
+        for (int i = 0; i < NHI; ++i)
+          for (int j = 0; j < NHI; ++j) {
+            double acc = Cp[i * N + j];
+            for (int p = 0; p < NLO; ++p)
+              for (int q = 0; q < NLO; ++q) acc -= Cp[i * N + NHI + p] * m[p][NLO + q] * Cp[(NHI + q) * N + j];
+            Sp[i * NHI + j] = acc;
+          }
+      }
+      for (int idx = lane; idx < NB_HI; idx += 32) {
+        double acc = 0.0;
+        for (int i = 0; i < NHI; ++i)
+          for (int j = 0; j < NHI; ++j)
+            acc += (double)(((idx >> (2 * (NHI - 1 - i))) & 3) - 1) * Cp[i * N + j] * (double)(((idx >> (2 * (NHI - 1 - j))) & 3) - 1);
+        Qh[idx] = acc;
+      }
+      for (int idx = lane; idx < NB_LO; idx += 32) {
+        double acc = 0.0;
+        for (int i = 0; i < NLO; ++i)
+          for (int j = 0; j < NLO; ++j)
+            acc += (double)(((idx >> (2 * (NLO - 1 - i))) & 3) - 1) * Cp[(NHI + i) * N + NHI + j] *
+                   (double)(((idx >> (2 * (NLO - 1 - j))) & 3) - 1);
+        Ql[idx] = acc;
+      }
+      __syncwarp();
+    }
 
     {
       {
@@ -214,7 +292,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           __syncwarp();
           double f[N], r[N], h[N];
 #pragma unroll
-          for (int j = 0; j < N; ++j) { f[j] = fs[j]; r[j] = ns[j]; h[j] = hs[j]; }
+          for (int j = 0; j < N; ++j) { const int d = pm[j]; f[j] = fs[d]; r[j] = ns[d]; h[j] = hs[d]; }   // permuted order
           double E0 = 0.0;
 #pragma unroll
           for (int j = 0; j < N; ++j) E0 = fma(r[j], h[j], E0);
@@ -259,7 +337,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
                 for (int p = 0; p < NHI; ++p) {
                   double s = 0.0;
 #pragma unroll
-                  for (int q = 0; q < NHI; ++q) s = fma(rec[L.o_schur + p * NHI + q], zh[q], s);
+                  for (int q = 0; q < NHI; ++q) s = fma(Sp[p * NHI + q], zh[q], s);
                   v = fma(zh[p], s, v);
                 }
               }
@@ -285,7 +363,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
             for (int i = 0; i < HI_IT; ++i)
               if (mb == i * 32 + lane) lb[i] = INF;
             // block constants: base = E0 + 2 x.h_hi + Qhh[x];  c_k = 2 (h_lo[k] + sum_j C[lo k][hi j] x_j)
-            double base = E0 + rec[L.o_qhh + mb];
+            double base = E0 + Qh[mb];
             double c[NLO];
 #pragma unroll
             for (int k = 0; k < NLO; ++k) c[k] = h[NHI + k];
@@ -294,7 +372,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               const double xj = (double)(((mb >> (2 * (NHI - 1 - j))) & 3) - 1);
               base = fma(2.0 * xj, h[j], base);
 #pragma unroll
-              for (int k = 0; k < NLO; ++k) c[k] = fma(C[(NHI + k) * N + j], xj, c[k]);
+              for (int k = 0; k < NLO; ++k) c[k] = fma(Cp[(NHI + k) * N + j], xj, c[k]);
             }
 #pragma unroll 1
             for (int i = 0; i < LO_IT; ++i) {
@@ -302,7 +380,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               const bool ok = (lo_valid >> i) & 1u;
               double e = INF;
               if (ok) {
-                e = base + rec[L.o_qll + b];
+                e = base + Ql[b];
 #pragma unroll
                 for (int k = 0; k < NLO; ++k) e = fma(2.0 * (double)(((b >> (2 * (NLO - 1 - k))) & 3) - 1), c[k], e);
               }
@@ -334,7 +412,8 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           uint64_t key = 0;
 #pragma unroll
           for (int j = 0; j < N; ++j) {
-            st[j] = (lidx < 0) ? 0.0 : f[j] + (double)(((lidx >> (2 * (N - 1 - j))) & 3) - 1);
+            // dot j sits at permuted position pm[8 + j]: its digit is read there
+            st[j] = (lidx < 0) ? 0.0 : fs[j] + (double)(((lidx >> (2 * (N - 1 - pm[8 + j]))) & 3) - 1);
             key |= (uint64_t)((unsigned)(int)st[j] & 0xffu) << (8 * j);
           }
           double Fm = 0.0;

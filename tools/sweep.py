@@ -64,6 +64,42 @@ def main():
     eng = Engine(0)
     out = {"gpu": torch.cuda.get_device_name(0), "flags": "latching + white/telegraph/radial noise, T=0"}
 
+    # ---- config 1: single-scan latency through the drop-in class ----
+    import time
+    import qarray
+    m = qarray.ChargeSensedDotArray(Cdd=[[0, .12], [.12, 0]], Cgd=[[1.0, .35, 0], [.3, .97, 0]], Cds=[[.04, .045]],
+                                    Cgs=[[6e-5, 3e-5, .98]], coulomb_peak_width=0.15, T=0.0, algorithm="default",
+                                    implementation="jax", max_charge_carriers=4)
+    for _ in range(20):
+        m.do2d_open(1, -3.3, 0.7, 64, 2, -3.1, 0.9, 64)
+    t0 = time.perf_counter()
+    for _ in range(200):
+        m.do2d_open(1, -3.3, 0.7, 64, 2, -3.1, 0.9, 64)
+    lat = (time.perf_counter() - t0) / 200
+    from oracle import cport
+    from qdsim.engine import new_scans
+    mb1 = m._model_batch()
+    s1 = new_scans(1)
+    v0, dx, dy = m.gate_voltage_composer.affine2d(1, -3.3, 0.7, 64, 2, -3.1, 0.9, 64)
+    s1["v0"][0, :3], s1["dx"][0, :3], s1["dy"][0, :3], s1["nx"], s1["ny"], s1["peak_width"] = v0, dx, dy, 64, 64, 0.15
+    cport.run_scans(mb1, s1, 0, threads=os.cpu_count())
+    _, _, dt_cpu = cport.run_scans(mb1, s1, 0, threads=os.cpu_count())
+    _, _, dt_cpu1 = cport.run_scans(mb1, s1, 0, threads=1)
+    out["config1_2dot_64x64_single_do2d_open"] = {
+        "gpu_call_latency_us": lat * 1e6, "note": "Python do2d_open -> qd_scan_open_host, host buffers, synchronous",
+        "cpu_cport_all_cores_us": dt_cpu * 1e6, "cpu_cport_1_core_us": dt_cpu1 * 1e6}
+
+    # ---- config 4 variant: thermal (T ~ U[50, 200] mK as the reference samples it), non-integer occupations ----
+    from qdsim import FLAG_THERMAL
+    global FLAGS
+    dev = synth.sample_devices(2048, 8, seed=8)
+    mbt = synth.model_batch(dev, thermal=True)
+    sct = synth.env_step_scans(mbt, dev, res=64, seed=9)
+    keep = FLAGS
+    FLAGS = FLAGS | FLAG_THERMAL
+    out["config4_variant_8dot_2048env_thermal"] = time_gpu(eng, mbt, sct, N_F32)
+    FLAGS = keep
+
     # ---- config 2 ----
     dev = synth.sample_devices(1024, 4, seed=2)
     mb = synth.model_batch(dev)
