@@ -58,9 +58,17 @@ class Scan:
 def simulate_scan(m: Model, s: Scan, latch_compare: str = "rounded", carry_rows: bool = False,
                   white_on: str = "input", return_margin: bool = False):
     """Returns ``(z (ny, nx) float64, n (ny, nx, N) float64[, margin (ny, nx)])``."""
-    ny, nx = s.ny, s.nx
+    v = composer.affine_grid(s.v0, s.dx, s.dy, s.nx, s.ny)
+    return simulate_points(m, v, s, latch_compare, carry_rows, white_on, return_margin)
+
+
+def simulate_points(m: Model, v, s: Scan, latch_compare: str = "rounded", carry_rows: bool = False,
+                    white_on: str = "input", return_margin: bool = False):
+    """Same on an explicit voltage array ``v`` (ny, nx, n_volt); ``s`` supplies peak width, seed and radial fields."""
+    v = np.asarray(v, dtype=np.float64)
+    ny, nx = v.shape[:2]
     n_dot = m.cdd_inv.shape[0]
-    v = composer.affine_grid(s.v0, s.dx, s.dy, nx, ny).reshape(ny * nx, -1)
+    v = v.reshape(ny * nx, -1)
     if m.algorithm == "tunnel":
         from . import path_b
         n, margin = path_b.ground_state_open(m, v, return_gap=True)     # "margin" = spectral gap of the pixel
