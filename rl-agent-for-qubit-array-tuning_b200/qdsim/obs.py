@@ -13,13 +13,13 @@ from ._lib import FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_NONE
 from .engine import Engine, ModelBatch, new_scans
 
 
-def obs_scans(mb: ModelBatch, gate_voltages, sensor_voltage, vgm, origin, obs_min: float, obs_max: float, res: int,
+def obs_scans(mb: ModelBatch, gate_voltages, sensor_voltage, vgm, origin, obs_min, obs_max, res: int,
               barrier_voltages=None, peak_width=0.1, peak_width_alpha=None, virtual: bool = True,
               gate_ground_truth=None, radial: dict | None = None, seeds=None):
     """Scan descriptors of one env.step for every env (env-major, N-1 adjacent pairs each).
 
     gate_voltages (E, N); sensor_voltage scalar or (E,); vgm (E, G, G); origin (E, G); barrier_voltages (E, B) for the
-    tunnel path.  ``virtual=True`` is the facade's barrier-mode call (``do2d('vP{i}', ..., 'vP{i+1}', ...,
+    tunnel path; obs_min / obs_max scalar or (E,) (the env draws its window half-width per episode, env.py:160-172).  ``virtual=True`` is the facade's barrier-mode call (``do2d('vP{i}', ..., 'vP{i+1}', ...,
     gate_voltages, add_full_crosstalk=True)``, :143-154); ``virtual=False`` its non-barrier call (physical gates i, i+1,
     every other gate at 0, :128-137).  ``radial``: dict(zero_radius (E,), ramp_distance (E,), full_noise_distance (E,) or
     None, max_amplitude) as sampled at :409-441.  ``peak_width_alpha``: VaryPeakWidth (utils/vary_peak_width.py).
@@ -32,7 +32,9 @@ def obs_scans(mb: ModelBatch, gate_voltages, sensor_voltage, vgm, origin, obs_mi
     env = np.repeat(np.arange(E), N - 1)
     ch = np.tile(np.arange(N - 1), E)
     rows = np.arange(n_scan)
-    step = (obs_max - obs_min) / (res - 1) if res > 1 else 0.0
+    obs_min = np.broadcast_to(np.asarray(obs_min, dtype=np.float64), (E,))[env]       # scalar or per env (window_delta)
+    obs_max = np.broadcast_to(np.asarray(obs_max, dtype=np.float64), (E,))[env]
+    step = (obs_max - obs_min) / (res - 1) if res > 1 else np.zeros(n_scan)
     scans = new_scans(n_scan)
     v1, v2 = gv[env, ch], gv[env, ch + 1]
     if virtual:
@@ -43,8 +45,8 @@ def obs_scans(mb: ModelBatch, gate_voltages, sensor_voltage, vgm, origin, obs_mi
         base[rows, ch] = v1 + obs_min
         base[rows, ch + 1] = v2 + obs_min
         scans["v0"][:, :G] = np.einsum("sij,sj->si", vgm[env], base) + origin[env]
-        scans["dx"][:, :G] = vgm[env, :, ch] * step
-        scans["dy"][:, :G] = vgm[env, :, ch + 1] * step
+        scans["dx"][:, :G] = vgm[env, :, ch] * step[:, None]
+        scans["dy"][:, :G] = vgm[env, :, ch + 1] * step[:, None]
     else:
         scans["v0"][rows, ch] = v1 + obs_min
         scans["v0"][rows, ch + 1] = v2 + obs_min

@@ -92,3 +92,28 @@ def test_observe_batch_end_to_end(engine):
         want = np.clip((z_ref[e] - p_low) / (p_high - p_low), 0, 1)
         np.testing.assert_allclose(img[e].cpu().numpy(), want, rtol=0, atol=5e-6)
     assert img.min().item() == 0.0 and img.max().item() == 1.0
+
+
+@pytest.mark.gpu
+def test_batched_env_shell_runs_episodes_on_the_gpu(engine):
+    import torch
+    from qdsim.vector_env import BatchedDeviceEnv, EnvConfig
+    env = BatchedDeviceEnv(48, 4, engine=engine, config=EnvConfig(resolution=24, max_steps=3), seed=5)
+    obs0, info = env.reset()
+    assert obs0["image"].shape == (48, 3, 24, 24) and obs0["image"].is_cuda
+    assert float(obs0["image"].min()) >= 0.0 and float(obs0["image"].max()) <= 1.0
+    assert np.abs(obs0["obs_gate_voltages"]).max() <= 1.0 + 1e-6
+    rng = np.random.default_rng(0)
+    for k in range(3):
+        o, r, term, trunc, info = env.step(rng.uniform(-1, 1, (48, 4)), rng.uniform(-1, 1, (48, 3)))
+        assert o["image"].shape == (48, 3, 24, 24) and torch.isfinite(o["image"]).all()
+        assert r["gates"].shape == (48, 4) and r["barriers"].shape == (48, 3)
+        assert ((r["gates"] >= 0) & (r["gates"] <= 1)).all()
+        assert trunc.all() == (k == 2) and not term.any()
+    # steering every env to its ground truth gives full reward and a structured (non-noise) image
+    gt_g = (info["gate_ground_truth"] - env.plunger_min) / (env.plunger_max - env.plunger_min) * 2 - 1
+    gt_b = (info["barrier_ground_truth"] - env.barrier_min) / (env.barrier_max - env.barrier_min) * 2 - 1
+    o, r, *_ = env.step(gt_g, gt_b)
+    assert np.allclose(r["gates"], 1.0) and np.allclose(r["barriers"], 1.0, atol=1e-5)
+    # far from the ground truth most scans are replaced by white noise (radial rule), near it none are
+    assert (env._scans()["rad_mode"] == 1).all()
