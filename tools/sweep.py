@@ -100,6 +100,24 @@ def main():
     out["config4_variant_8dot_2048env_thermal"] = time_gpu(eng, mbt, sct, N_F32)
     FLAGS = keep
 
+    # ---- batched env shell (first "next" row): whole env.step incl. host logic, scans, device normalisation ----
+    from qdsim.vector_env import BatchedDeviceEnv, EnvConfig
+    shell = {}
+    for n_dot, n_env in ((4, 1024), (8, 256)):
+        env = BatchedDeviceEnv(n_env, n_dot, engine=eng, config=EnvConfig(resolution=64, max_steps=50), seed=1)
+        env.reset()
+        rng = np.random.default_rng(0)
+        acts = [(rng.uniform(-0.1, 0.1, (n_env, n_dot)), rng.uniform(-0.1, 0.1, (n_env, n_dot - 1))) for _ in range(4)]
+        env.step(*acts[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for a in acts[1:]:
+            env.step(*a)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        shell[f"{n_dot}dot_{n_env}env_64x64_tunnel"] = {"ms_per_step": dt * 1e3, "env_steps_per_s": n_env / dt}
+    out["batched_env_shell"] = shell
+
     # ---- config 2 ----
     dev = synth.sample_devices(1024, 4, seed=2)
     mb = synth.model_batch(dev)
