@@ -2,8 +2,7 @@
 // (src/qarray_latched/DotArrays/ground_state.py:24-166; restated in oracle/path_b.py).  sm_100a, one WARP per pixel:
 // the 32-state truncated basis maps one basis state to one lane.
 //
-// Per pixel (all 32 lanes cooperate; pixels of a row are processed in order, so latching and the telegraph chain are
-// plain sequential state):
+// Per pixel (all 32 lanes cooperate):
 //   1. dot potentials g = cgd[:N] v, continuous relaxation (closed form, or the reference's 50 projected-gradient steps).
 //   2. 4^N candidates floor(n_c) + {-1,0,1,2}^N.  E = z^T C z, z = r + delta.  The digits split into a high and a low
 //      half (<= 256 combinations each).  A block = one high combination: its 256 low candidates cost ~8 instructions
@@ -100,8 +99,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
   double* ll = qi + 32;
   double* yy = ll + 32;
   double* vq = yy + 32;          // interleaved (v_j, q_j) of the current Householder step, 64 doubles
-  double* qs = vq + 32;
-  double* sv = qs + 64;          // small vectors: vv[16] gs[8] ns[8] fs[8] hs[8] ts[8] nb[8]
+  double* sv = vq + 96;          // (one spare row) small vectors: vv[16] gs[8] ns[8] fs[8] hs[8] ts[8] nb[8]
   double* vv = sv;
   double* gs = sv + 16;
   double* ns = sv + 24;
@@ -235,15 +233,13 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
                            : a.points[(size_t)pix * NV + lane];
           }
           __syncwarp();
-          double us = 0.0;
           {
-            double acc = 0.0;
-            if (lane <= N) {
-              const double* arow = (lane < N) ? rec + L.o_a + lane * NV : rec + L.o_sa;
+            if (lane < N) {
+              double acc = 0.0;
+              const double* arow = rec + L.o_a + lane * NV;
               for (int k = 0; k < NV; ++k) acc = fma(arow[k], vv[k], acc);
+              gs[lane] = acc;
             }
-            if (lane < N) gs[lane] = acc;
-            us = shfl_f64(acc, N);
             if (lane >= 16 && lane < 16 + B) {
               const int d = lane - 16;
               double t = par[QD_PAR_TC_BASE];
