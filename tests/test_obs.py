@@ -117,3 +117,35 @@ def test_batched_env_shell_runs_episodes_on_the_gpu(engine):
     assert np.allclose(r["gates"], 1.0) and np.allclose(r["barriers"], 1.0, atol=1e-5)
     # far from the ground truth most scans are replaced by white noise (radial rule), near it none are
     assert (env._scans()["rad_mode"] == 1).all()
+
+
+def test_agent_views_follow_the_reference_channel_and_transpose_rule():
+    """Literal per-env transcription of multi_agent_wrapper.py:147-178, 311-347 vs the batched torch views."""
+    import torch
+    from qdsim import agents
+    n_dot, E, H = 5, 3, 6
+    rng = np.random.default_rng(0)
+    image = rng.random((E, n_dot - 1, H, H)).astype(np.float32)           # [env, pair, iy, ix]
+    obs = {"image": torch.from_numpy(image), "obs_gate_voltages": rng.random((E, n_dot)).astype(np.float32),
+           "obs_barrier_voltages": rng.random((E, n_dot - 1)).astype(np.float32)}
+    views = agents.agent_observations(obs, n_dot)
+    assert list(views) == [f"plunger_{i}" for i in range(5)] + [f"barrier_{j}" for j in range(4)]
+    for e in range(E):
+        global_image = np.transpose(image[e], (1, 2, 0))                    # the reference's (H, W, N-1)
+        for i in range(n_dot):
+            ch = [0, 0] if i == 0 else [n_dot - 2, n_dot - 2] if i == n_dot - 1 else [i - 1, i]
+            img1, img2 = global_image[:, :, ch[0]], global_image[:, :, ch[1]]
+            if i == n_dot - 1:
+                img1, img2 = img1.T, img2.T
+            elif i != 0:
+                img2 = img2.T
+            want = np.stack([img1, img2], axis=2)                          # (H, W, 2)
+            got = views[f"plunger_{i}"]["image"][e].numpy()                # (2, H, W)
+            assert np.array_equal(np.transpose(got, (1, 2, 0)), want)
+            assert views[f"plunger_{i}"]["voltage"][e, 0] == obs["obs_gate_voltages"][e, i]
+        for j in range(n_dot - 1):
+            got = views[f"barrier_{j}"]["image"][e].numpy()
+            assert np.array_equal(got[0], global_image[:, :, j])
+            assert views[f"barrier_{j}"]["voltage"][e, 0] == obs["obs_barrier_voltages"][e, j]
+    # views, not copies, for the single-channel agents
+    assert views["barrier_2"]["image"].data_ptr() == obs["image"][:, 2:3].data_ptr()
