@@ -1,0 +1,117 @@
+"""Golden vectors made by the REFERENCE ITSELF, run in this container (needs /root/reference; the fixtures travel, the
+reference does not):
+
+    python tests/golden/make_reference_golden.py
+
+The reference's tunnel-coupled simulator (Path B, what ``env.step`` executes) is in-tree Python
+(/root/reference/src/qarray_latched/DotArrays/*.py).  It is imported unmodified through ``refshim`` (eager NumPy
+evaluation of its jax calls, inert shims for the absent ``qarray`` type names), constructed exactly like
+``QarrayBaseClass._load_model_with_barriers`` does (src/qadapt/environment/qarray_base_class.py:817-838) and driven
+exactly like ``_get_charge_sensor_data`` does (:143-163): ``gate_voltage_composer.do2d('vP#', ..., gate_voltages,
+add_full_crosstalk=True)`` -> ``charge_sensor_open(vg_flat, vb)``.  No latching / noise model (those classes live in
+the absent wheel), so every number in these files comes from reference code.
+
+Each ``ref_*.npz`` holds the raw inputs (non-Maxwell capacitances, barrier model, virtual gate matrix, window) and the
+reference's outputs: ``cdd_inv_full`` / ``cgd_full`` (Maxwell conversion, S1), ``vg`` (scan grid, S2), ``n`` (ground
+state occupations, B1-B6), ``z`` (sensor signal, S3/S4).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+for p in (HERE, ROOT, os.path.join(ROOT, "rl-agent-for-qubit-array-tuning_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+# name: (n_dot, res, seed, pair (1-based left dot), vgm kind, with_cbb, barriers?)
+CASES = {
+    "ref_4dot_tunnel_identity_vgm": dict(n_dot=4, res=32, seed=11, pair=2, vgm="identity", cbb=False),
+    "ref_4dot_tunnel_perfect_vgm_cbb": dict(n_dot=4, res=20, seed=12, pair=1, vgm="perfect", cbb=True),
+    "ref_5dot_tunnel_low_occupancy": dict(n_dot=5, res=16, seed=13, pair=3, vgm="identity", cbb=False, offset=-1.2),
+    "ref_6dot_tunnel_identity_vgm": dict(n_dot=6, res=16, seed=14, pair=4, vgm="identity", cbb=True),
+    "ref_8dot_tunnel_identity_vgm": dict(n_dot=8, res=12, seed=15, pair=5, vgm="identity", cbb=False),
+    "ref_4dot_constant_tc_no_barriers": dict(n_dot=4, res=16, seed=16, pair=1, vgm="identity", cbb=False, barriers=False),
+}
+
+
+def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True):
+    """Raw inputs of one case, drawn with the reference's sampling ranges (qdsim.synth)."""
+    from qdsim import synth
+    dev = synth.sample_barrier_devices(1, n_dot, seed=seed)
+    rng = np.random.default_rng([seed, 5])
+    raw = {k: dev[k][0] for k in ("Cdd", "Cgd", "Cds", "Cgs", "Cbd", "Cbg", "Cbs")}
+    B = n_dot - 1
+    raw["Cbb"] = None
+    if cbb:                                              # qarray_config.yaml Cbb ranges are irrelevant: the term is 0
+        c = np.triu(rng.uniform(0.01, 0.05, size=(B, B)), 1)
+        raw["Cbb"] = c + c.T
+    raw.update(tc_base=float(dev["tc_base"][0]), alpha=dev["alpha"][0], peak_width=float(dev["peak_width"][0]),
+               T=float(dev["T"][0]), tc=0.7, barriers=barriers)
+    raw["barrier_voltages"] = rng.uniform(-1.0, 3.0, size=B)
+    raw["half"] = float(rng.uniform(1.5, 2.0))
+    raw["centre_offset"] = rng.uniform(-2.0, 2.0, size=n_dot) + offset
+    raw.update(res=res, pair=pair, vgm_kind=vgm)
+    return raw
+
+
+def run_reference(raw):
+    """-> dict of the reference's outputs for one case."""
+    from refshim import reference_modules
+    n_dot = raw["Cdd"].shape[0]
+    with reference_modules() as ref:
+        kw = {}
+        if raw["barriers"]:
+            kw = dict(Cbd=raw["Cbd"], Cbg=raw["Cbg"], Cbs=raw["Cbs"], Cbb=raw["Cbb"],
+                      barrier_model=ref.BarrierVoltageModel(n_barrier=n_dot - 1, n_dot=n_dot, tc_base=raw["tc_base"],
+                                                            alpha=list(raw["alpha"])))
+        model = ref.TunnelCoupledChargeSensed(
+            Cdd=raw["Cdd"], Cgd=raw["Cgd"], Cds=raw["Cds"], Cgs=raw["Cgs"], coulomb_peak_width=raw["peak_width"],
+            T=raw["T"], max_charge_carriers=4, tc=raw["tc"], noise_model=None, latching_model=None,
+            voltage_capacitance_model=None, use_sparse=False, num_charge_states=32, charge_state_batch_size=1000,
+            charge_carrier="electrons", **kw)
+        comp = model.gate_voltage_composer
+        perfect_vgm = np.array(comp.virtual_gate_matrix)
+        if raw["vgm_kind"] == "identity":                # qarray_base_class.py:868-877 (electrons: -I)
+            comp.virtual_gate_matrix = -np.eye(model.n_gate)
+        # ground truth in virtual coordinates: solve with the reference's own matrices (no upstream optimal_Vg here)
+        n_target = np.concatenate([np.ones(n_dot), [0.53]])
+        vg_gt = np.linalg.solve(model.cgd_full[:, :model.n_gate], n_target)     # continuous minimum == n_target
+        vd_gt = np.linalg.solve(np.array(comp.virtual_gate_matrix), vg_gt - np.array(comp.virtual_gate_origin))
+        gate_voltages = vd_gt.copy()
+        gate_voltages[:n_dot] += raw["centre_offset"]
+        g1 = raw["pair"]
+        v1, v2, half, res = gate_voltages[g1 - 1], gate_voltages[g1], raw["half"], raw["res"]
+        vg = comp.do2d(f"vP{g1}", v1 - half, v1 + half, res, f"vP{g1 + 1}", v2 - half, v2 + half, res,
+                       gate_voltages, True)
+        vg_flat = vg.reshape(-1, vg.shape[-1])
+        if raw["barriers"]:
+            vb = np.full((vg_flat.shape[0], n_dot - 1), raw["barrier_voltages"])
+            z, n = model.charge_sensor_open(vg_flat, vb)
+        else:
+            z, n = model.charge_sensor_open(vg_flat)
+        return dict(cdd_full=np.array(model.cdd_full), cdd_inv_full=np.array(model.cdd_inv_full),
+                    cgd_full=np.array(model.cgd_full), perfect_vgm=perfect_vgm,
+                    vgm=np.array(comp.virtual_gate_matrix), origin=np.array(comp.virtual_gate_origin),
+                    gate_voltages=gate_voltages, window=np.array([v1 - half, v1 + half, v2 - half, v2 + half]),
+                    vg=np.array(vg), z=np.array(z, dtype=np.float64).reshape(res, res),
+                    n=np.array(n, dtype=np.float64).reshape(res, res, n_dot))
+
+
+def main(only=None):
+    for name, spec in CASES.items():
+        if only and name not in only:
+            continue
+        raw = case_inputs(**spec)
+        out = run_reference(raw)
+        save = {k: v for k, v in raw.items() if v is not None}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **save, **out)
+        n = out["n"]
+        print(f"{name}: n range [{n.min():.3f}, {n.max():.3f}], z range [{out['z'].min():.4f}, {out['z'].max():.4f}], "
+              f"non-integer pixels {(np.abs(n - np.rint(n)).max(axis=-1) > 1e-3).mean():.2f}", flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:])
