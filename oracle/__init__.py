@@ -5,7 +5,18 @@ THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only ``tests/``, ``__graft_entry
 (``rl-agent-for-qubit-array-tuning_b200/``) never imports ``oracle`` and fails loudly when the CUDA
 library is missing.
 
-PARITY UNPINNED.  The arithmetic of "Path A" lives in the third-party package ``qarray==1.6.0`` (+
+PARITY STATUS, by stage (details: DESIGN.md section 2).
+
+* PINNED against the reference itself, run in this container (``tests/golden/ref_*.npz`` made by
+  ``tests/golden/make_reference_golden.py``; checked by ``tests/test_reference_golden.py``): Maxwell conversion, scan
+  grids, optimal gate voltages / virtual gate matrix, the whole tunnel-coupled "Path B" ground state
+  (``src/qarray_latched/DotArrays/*.py`` executed unmodified) and the sensor stack; for "Path A" the free energy and
+  floor/ceil candidate enumeration through the reference's in-tree mirrors (``src/qarray_latched/functions.py:30-47``)
+  with the relaxation QP of ``functions.py:66-81`` solved exactly.
+* PARITY UNPINNED for what only exists in the absent wheel: the ADMM/OSQP solver tolerance of the relaxation, the
+  thresholded / brute-force variants, ``LatchingModel``, ``WhiteNoise``, ``TelegraphNoise``.
+
+The arithmetic of "Path A" lives in the third-party package ``qarray==1.6.0`` (+
 ``qarray-rust-core==1.3.1``), pinned by the reference at ``pyproject.toml:8`` / ``uv.lock:2015-2053`` but absent
 from ``/root/reference`` and from this image; the reference ships no test that pins a number on this path
 (SURVEY.md section 4).  The oracle therefore restates

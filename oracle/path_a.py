@@ -1,7 +1,11 @@
 """Path A: constant-interaction open-array ground state.
 
-Test infrastructure (see ``oracle/__init__.py``).  PARITY UNPINNED: the algorithm is qarray==1.6.0's
-``ground_state_open`` (absent from /root/reference).  Restated from its published form and anchored on:
+Test infrastructure (see ``oracle/__init__.py``).  The algorithm is qarray==1.6.0's ``ground_state_open`` (absent from
+/root/reference).  PARTLY PINNED: the ``default`` algorithm at T = 0 reproduces, bit for bit, fixtures made by executing
+the reference's in-tree mirrors of the upstream functions (free energy + floor/ceil enumeration,
+src/qarray_latched/functions.py:30-47) on the exact solution of the reference's relaxation QP (functions.py:66-81) --
+``tests/golden/ref_a_*.npz``, ``tests/test_reference_golden.py``.  PARITY UNPINNED for the rest (solver tolerance of the
+ADMM/OSQP relaxation, ``thresholded``, ``brute_force``, ``T > 0``).  Restated from its published form and anchored on:
 
 * the reference's call site  src/qadapt/environment/qarray_base_class.py:744-756 (``algorithm``, ``implementation``,
   ``max_charge_carriers``, ``T`` passed through),

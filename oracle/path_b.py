@@ -17,7 +17,9 @@ literal, in NumPy fp64, following
                                                                   diagonal of a zero-diagonal matrix = 0;
                                                                   ``t = tc_base exp(-alpha vb_eff)``, no abs)
 
-It is "parity unpinned" only in the sense that no reference test pins numbers; the algorithm itself is read, not recalled.
+PINNED: ``tests/golden/ref_*tunnel*.npz`` hold the output of the reference's own code (the files above, executed unmodified
+on a NumPy stand-in for jax, ``tests/golden/refshim.py``); this restatement reproduces them to 5e-14
+(``tests/test_reference_golden.py``).
 ``T`` is read by the reference and never used on this path (ground_state.py:48).
 """
 from __future__ import annotations

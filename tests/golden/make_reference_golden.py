@@ -100,7 +100,92 @@ def run_reference(raw):
                     n=np.array(n, dtype=np.float64).reshape(res, res, n_dot))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Path A: the constant-interaction ground state lives in the absent qarray wheel, but the reference carries in-tree
+# mirrors of its pieces.  These goldens execute THOSE FUNCTIONS (compiled from the reference's own source text, nothing
+# copied): free_energy + open_charge_configurations_jax (src/qarray_latched/functions.py:30-47), convert_to_maxwell
+# (DotArrays/_helper_functions.py:129-164), GateVoltageComposer.do2d with physical gates (GateVoltageComposer.py:224-255),
+# optimal_Vg + compute_optimal_virtual_gate_matrix (src/qarray_latched/optimal_v_calc.py:10-44).  The one piece that
+# cannot run is the ADMM solver of the relaxation QP (jaxopt.BoxOSQP, functions.py:66-81): its PROBLEM is taken from
+# the reference (P = cdd_inv, q = -cdd_inv cgd vg, n >= 0) and solved exactly with scipy.optimize.nnls.
+# ---------------------------------------------------------------------------------------------------------------------
+CASES_A = {
+    "ref_a_2dot_64x64": dict(n_dot=2, res=64, seed=21, pair=1),
+    "ref_a_4dot_32x32": dict(n_dot=4, res=32, seed=22, pair=2),
+    "ref_a_6dot_20x20": dict(n_dot=6, res=20, seed=23, pair=3),
+    "ref_a_8dot_16x16": dict(n_dot=8, res=16, seed=24, pair=6),
+}
+
+
+def _reference_functions(path, names, namespace):
+    """Compile the named top-level functions of a reference source file into ``namespace`` (the file itself cannot be
+    imported: it needs jaxopt and plots at import time)."""
+    import ast
+    tree = ast.parse(open(path).read(), filename=path)
+    body = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in names]
+    assert {b.name for b in body} == set(names), [b.name for b in body]
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
+    return namespace
+
+
+def run_reference_path_a(n_dot, res, seed, pair):
+    from scipy.optimize import nnls
+    import refshim
+    from qdsim import synth
+    dev = synth.sample_devices(1, n_dot, seed=seed)
+    rng = np.random.default_rng([seed, 6])
+    Cdd, Cgd, Cds, Cgs = (dev[k][0] for k in ("Cdd", "Cgd", "Cds", "Cgs"))
+    with refshim.reference_modules() as ref:
+        import jax.numpy as jnp
+        helpers = sys.modules["qarray_latched.DotArrays._helper_functions"]
+        composer_mod = sys.modules["qarray_latched.DotArrays.GateVoltageComposer"]
+        fn = _reference_functions(os.path.join(refshim.REF_SRC, "qarray_latched", "functions.py"),
+                                  ["free_energy", "open_charge_configurations_jax"], {"jnp": jnp})
+        opt = _reference_functions(os.path.join(refshim.REF_SRC, "qarray_latched", "optimal_v_calc.py"),
+                                   ["optimal_Vg", "compute_optimal_virtual_gate_matrix"],
+                                   {"np": np, "CddInv": None, "Cgd_holes": None, "VectorList": None})
+        cdd, cdd_inv, cgd = (np.array(a) for a in helpers.convert_to_maxwell(Cdd, Cgd))
+        cdd_full, cdd_inv_full, cgd_full = (np.array(a) for a in helpers._convert_to_maxwell_with_sensor(Cdd, Cgd, Cds, Cgs))
+        n_target = np.concatenate([np.ones(n_dot), [0.53]])
+        vg_opt = opt["optimal_Vg"](cdd_inv_full, cgd_full, n_target, rcond=1e-3)
+        vgm_opt = opt["compute_optimal_virtual_gate_matrix"](cdd_inv_full, cgd_full)
+        comp = composer_mod.GateVoltageComposer(n_gate=n_dot + 1, n_dot=n_dot, n_sensor=1)
+        half = float(rng.uniform(1.5, 2.0))
+        centre = vg_opt[:n_dot] + rng.uniform(-2.5, 2.5, size=n_dot)       # holes convention: cgd = -Cgd, vg < 0 fills dots
+        x0, y0 = centre[pair - 1], centre[pair]
+        grid = comp.do2d(pair, x0 - half, x0 + half, res, pair + 1, y0 - half, y0 + half, res)
+        base = np.concatenate([centre, vg_opt[n_dot:]])
+        base[pair - 1] = base[pair] = 0.0
+        vg = grid + base                                                    # other plungers at their set point
+        r = np.linalg.cholesky(cdd_inv).T
+        flat = vg.reshape(-1, n_dot + 1)
+        n_c = np.empty((flat.shape[0], n_dot))
+        n_out = np.empty((flat.shape[0], n_dot))
+        margin = np.empty(flat.shape[0])
+        for i, v in enumerate(flat):
+            n_c[i] = nnls(r, r @ (cgd @ v), maxiter=200)[0]                  # the reference's QP, solved exactly
+            basis = fn["open_charge_configurations_jax"](jnp.array(n_c[i]))
+            energies = np.asarray(fn["free_energy"](v, cdd_inv, cgd, basis))
+            k = int(np.argmin(energies))
+            n_out[i] = basis[k]
+            e = np.sort(energies)
+            margin[i] = e[1] - e[0]
+    return dict(Cdd=Cdd, Cgd=Cgd, Cds=Cds, Cgs=Cgs, cdd=cdd, cdd_inv=cdd_inv, cgd=cgd, cdd_inv_full=cdd_inv_full,
+                cgd_full=cgd_full, vg_opt=vg_opt, vgm_opt=vgm_opt, n_target=n_target, base=base, pair=pair, res=res,
+                window=np.array([x0 - half, x0 + half, y0 - half, y0 + half]), vg=vg,
+                n_continuous=n_c.reshape(res, res, n_dot), n=n_out.reshape(res, res, n_dot),
+                margin=margin.reshape(res, res))
+
+
 def main(only=None):
+    for name, spec in CASES_A.items():
+        if only and name not in only:
+            continue
+        out = run_reference_path_a(**spec)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(f"{name}: n range [{out['n'].min():.0f}, {out['n'].max():.0f}], relaxed pixels "
+              f"{(out['vg'].reshape(-1, out['vg'].shape[-1]) @ out['cgd'].T < 0).any(axis=1).mean():.2f}, "
+              f"min margin {out['margin'].min():.2e}", flush=True)
     for name, spec in CASES.items():
         if only and name not in only:
             continue

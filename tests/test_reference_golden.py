@@ -188,3 +188,98 @@ def test_gpu_affine_scan_matches_reference(engine, name):
     n, z = n.reshape(res, res, -1), z.reshape(res, res)
     np.testing.assert_allclose(n[ok], d["n"][ok], rtol=0, atol=N_ATOL_GPU)
     np.testing.assert_allclose(z[ok], d["z"][ok], rtol=Z_RTOL_GPU, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Path A: fixtures made by executing the reference's in-tree mirrors of the absent qarray functions
+# (make_reference_golden.py::run_reference_path_a): free_energy + floor/ceil enumeration (qarray_latched/functions.py:30-47),
+# convert_to_maxwell, the physical-gate do2d grid, optimal_Vg / optimal virtual gate matrix (optimal_v_calc.py:10-44),
+# with the relaxation QP of functions.py:66-81 solved exactly (NNLS).  Integer charges: bit-exact outside exact ties.
+# ---------------------------------------------------------------------------------------------------------------------
+REF_A_CASES = ["ref_a_2dot_64x64", "ref_a_4dot_32x32", "ref_a_6dot_20x20", "ref_a_8dot_16x16"]
+TIE_TOL = 1e-9
+
+
+def load_a(name):
+    return dict(np.load(os.path.join(HERE, "golden", name + ".npz")))
+
+
+@pytest.mark.parametrize("name", REF_A_CASES)
+def test_path_a_host_code_matches_reference_mirrors(name):
+    from qdsim import maxwell
+    from qdsim.composer import GateVoltageComposer
+    d = load_a(name)
+    cdd, cdd_inv, cgd = maxwell.maxwell(d["Cdd"], d["Cgd"])
+    np.testing.assert_allclose(cdd, d["cdd"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(cdd_inv, d["cdd_inv"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(cgd, d["cgd"], rtol=0, atol=0)
+    cdd_nm, cgd_nm = maxwell.embed_sensor(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"])
+    _, cdd_inv_full, cgd_full = maxwell.maxwell(cdd_nm, cgd_nm)
+    np.testing.assert_allclose(cdd_inv_full, d["cdd_inv_full"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(maxwell.optimal_vg(cdd_inv_full, cgd_full, d["n_target"], 1e-3), d["vg_opt"],
+                               rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(maxwell.optimal_vgm(cdd_inv_full, cgd_full), d["vgm_opt"], rtol=1e-9, atol=1e-11)
+    n_dot, res, pair, w = d["Cdd"].shape[0], int(d["res"]), int(d["pair"]), d["window"]
+    comp = GateVoltageComposer(n_gate=n_dot + 1, n_dot=n_dot, n_sensor=1)
+    grid = comp.do2d(pair, w[0], w[1], res, pair + 1, w[2], w[3], res) + d["base"]
+    np.testing.assert_allclose(grid, d["vg"], rtol=1e-13, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", REF_A_CASES)
+def test_path_a_oracle_matches_reference_mirrors(name):
+    from oracle import path_a
+    d = load_a(name)
+    n_dot = d["Cdd"].shape[0]
+    vg = d["vg"].reshape(-1, n_dot + 1)
+    n_c = path_a.continuous_relaxation(vg @ d["cgd"].T, d["cdd"])
+    np.testing.assert_allclose(n_c, d["n_continuous"].reshape(-1, n_dot), rtol=0, atol=1e-9)     # exact LCP == exact QP
+    n, margin = path_a.ground_state_open(vg, d["cgd"], d["cdd_inv"], d["cdd"], "default", return_margin=True)
+    safe = d["margin"].reshape(-1) > TIE_TOL
+    assert safe.mean() > 0.995
+    assert np.array_equal(n[safe], d["n"].reshape(-1, n_dot)[safe])
+    np.testing.assert_allclose(margin[safe], d["margin"].reshape(-1)[safe], rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", REF_A_CASES)
+def test_path_a_cport_matches_reference_mirrors(name):
+    from oracle import cport
+    from qdsim import N_U8  # noqa: F401
+    from qdsim.engine import ModelBatch, new_scans
+    d = load_a(name)
+    n_dot, res = d["Cdd"].shape[0], int(d["res"])
+    mb = ModelBatch.from_capacitances(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"], algorithm="default")
+    s = _affine_scan_a(d, new_scans)
+    _, nc, _ = cport.run_scans(mb, s, 0, threads=2)
+    safe = d["margin"] > TIE_TOL
+    assert np.array_equal(nc.reshape(res, res, n_dot)[safe], d["n"][safe])
+
+
+def _affine_scan_a(d, new_scans):
+    from qdsim.composer import GateVoltageComposer
+    n_dot, res, pair, w = d["Cdd"].shape[0], int(d["res"]), int(d["pair"]), d["window"]
+    comp = GateVoltageComposer(n_gate=n_dot + 1, n_dot=n_dot, n_sensor=1)
+    v0, dx, dy = comp.affine2d(pair, w[0], w[1], res, pair + 1, w[2], w[3], res)
+    s = new_scans(1)
+    s["v0"][0, :n_dot + 1], s["dx"][0, :n_dot + 1], s["dy"][0, :n_dot + 1] = v0 + d["base"], dx, dy
+    s["nx"], s["ny"] = res, res
+    return s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", REF_A_CASES)
+def test_path_a_gpu_matches_reference_mirrors(engine, name):
+    """CUDA path, both entries: the drop-in class on the reference's explicit grid and the batched affine scan."""
+    from qarray import ChargeSensedDotArray
+    from qdsim import N_U8
+    from qdsim.engine import ModelBatch, new_scans
+    d = load_a(name)
+    n_dot, res = d["Cdd"].shape[0], int(d["res"])
+    safe = d["margin"] > TIE_TOL
+    model = ChargeSensedDotArray(Cdd=d["Cdd"], Cgd=d["Cgd"], Cds=d["Cds"], Cgs=d["Cgs"], coulomb_peak_width=0.2, T=0.0,
+                                 algorithm="default", implementation="jax", max_charge_carriers=4)
+    np.testing.assert_allclose(model.optimal_Vg(d["n_target"]), d["vg_opt"], rtol=1e-10, atol=1e-12)
+    n = model.ground_state_open(d["vg"])
+    assert np.array_equal(np.rint(n).astype(np.int64)[safe], d["n"].astype(np.int64)[safe])
+    engine.set_models(ModelBatch.from_capacitances(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"], algorithm="default"))
+    _, n2 = engine.scan_open_host(_affine_scan_a(d, new_scans), n_type=N_U8, flags=0)
+    assert np.array_equal(n2.reshape(res, res, n_dot).astype(np.int64)[safe], d["n"].astype(np.int64)[safe])
