@@ -5,8 +5,9 @@ Everything per-env that the reference does in Python per process (device samplin
 ground truth, the N-1 scans, percentile normalisation) is vectorised over the env axis on the host (NumPy, O(n_env N)
 numbers) or runs on the GPU (the scans and the normalisation: one ``qd_scan_open`` + one ``qd_normalise_obs`` per step
 for the whole batch).  Barrier mode only, like the reference env (env.py:61-62).  Virtual-gate update methods:
-``None`` (VGM stays -I for electrons, env.py:179) and ``"perfect"`` (env.py:181-182); the CNN + Kalman update needs the
-trained checkpoint and stays on top, outside this path.
+``None`` (VGM stays -I for electrons, env.py:179), ``"perfect"`` (env.py:181-182) and ``"kalman"`` / ``"direct"``
+(env.py:537-621): one CNN forward over the batch's ``n_env (N-1)`` device-resident scans, the batched scalar filter and
+a batched pseudo-inverse (``qdsim.virtualisation``) after every observation, as the reference does per env.
 
 Observation layout: ``image`` is a CUDA float32 tensor ``[n_env, N-1, res, res]`` (channels first; the reference's
 per-env image is ``(res, res, N-1)``), voltages are NumPy ``[n_env, N]`` / ``[n_env, N-1]`` in [-1, 1].
@@ -45,7 +46,10 @@ class EnvConfig:
     optimal_vg_center: tuple = (1.0, 0.53)      # dots, sensor (qarray_config.yaml:122)
     optimal_tc: float = 1e-3                    # qarray_config.yaml:125
     electrons: bool = True                      # charge_carrier_type (qarray_config.yaml:118)
-    update_method: str | None = None            # None | "perfect"
+    update_method: str | None = None            # None | "perfect" | "kalman" | "direct" (env_config.yaml:61)
+    nearest_neighbour: bool = False             # CNN outputs [RL, LR] instead of [NN, NNN_right, NNN_left] (:62)
+    variance_threshold: float = 0.05            # :65
+    process_noise: float = 0.0                  # :66
 
 
 def gate_reward(dist, cfg: EnvConfig):
@@ -84,9 +88,24 @@ def barrier_reward(dist, cfg: EnvConfig):
 class BatchedDeviceEnv:
     """``n_env`` independent tuning environments stepped together on one GPU."""
 
-    def __init__(self, n_env: int, num_dots: int, engine=None, config: EnvConfig | None = None, seed: int = 0):
+    def __init__(self, n_env: int, num_dots: int, engine=None, config: EnvConfig | None = None, seed: int = 0,
+                 capacitance_model=None):
+        """``capacitance_model``: torch module ``images [B, 1, res, res] -> (values, log_vars) [B, K]`` (the reference's
+        ``CapacitancePredictionModel`` contract); required for ``update_method`` kalman / direct."""
         self.n_env, self.num_dots = n_env, num_dots
         self.cfg = config or EnvConfig()
+        self.vg_updater = None
+        if self.cfg.update_method in ("kalman", "direct"):
+            if capacitance_model is None:
+                raise ValueError("Capacitance model weights must be provided via capacitance_model when using "
+                                 f"update_method '{self.cfg.update_method}'.")
+            from .virtualisation import VirtualGateUpdater
+            self.vg_updater = VirtualGateUpdater(
+                n_env, num_dots, capacitance_model, method=self.cfg.update_method,
+                nearest_neighbour=self.cfg.nearest_neighbour, variance_threshold=self.cfg.variance_threshold,
+                process_noise=self.cfg.process_noise, electrons=self.cfg.electrons)
+        elif self.cfg.update_method not in (None, "perfect"):
+            raise ValueError(f"Unknown update method: {self.cfg.update_method}")
         self.eng = engine
         self.rng = np.random.default_rng(seed)
         self.seed = seed
@@ -170,6 +189,8 @@ class BatchedDeviceEnv:
             self.z_dev = torch.empty(E * (N - 1) * res * res, dtype=torch.float32, device=f"cuda:{self.eng.device}")
         flags = FLAG_LATCH | FLAG_NOISE | (FLAG_RADIAL if self.radial else 0)
         image = obs.observe(self.eng, self._scans(), self.z_dev, flags=flags, normalise=True)
+        if self.vg_updater is not None:                    # env.py:229 / :292: update right after the observation
+            self.vgm, self.cgd_estimate = self.vg_updater.update(image, self.mb.cdd_inv_full)
         g, b = self._normalised_voltages()
         return {"image": image, "obs_gate_voltages": g, "obs_barrier_voltages": b}
 
@@ -178,6 +199,8 @@ class BatchedDeviceEnv:
         self._episode += 1
         self.step_count = 0
         self._sample()
+        if self.vg_updater is not None:
+            self.vg_updater.reset()
         self.gate_gt, self.barrier_gt, self.sensor_gt = self._ground_truth()
         self._init_voltage_ranges()
         if self.eng is not None:

@@ -122,7 +122,7 @@ def _reference_functions(path, names, namespace):
     imported: it needs jaxopt and plots at import time)."""
     import ast
     tree = ast.parse(open(path).read(), filename=path)
-    body = [node for node in tree.body if isinstance(node, ast.FunctionDef) and node.name in names]
+    body = [node for node in ast.walk(tree) if isinstance(node, ast.FunctionDef) and node.name in names]
     assert {b.name for b in body} == set(names), [b.name for b in body]
     exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), namespace)
     return namespace
@@ -177,7 +177,72 @@ def run_reference_path_a(n_dot, res, seed, pair):
                 margin=margin.reshape(res, res))
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Virtualisation in the loop: the reference's Kalman / direct updaters are plain NumPy and import as
+# they are; the VGM update is a method of QarrayBaseClass (which cannot be imported: it needs the qarray wheel), so the
+# two methods are compiled from the reference's source text and called on a stand-in ``self``.
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference_virtualisation(n_env=5, n_dot=6, n_step=8, seed=31):
+    import importlib.util
+    import types
+    import refshim
+    from qdsim import synth
+    rng = np.random.default_rng(seed)
+    base = os.path.join(refshim.REF_SRC, "qadapt", "capacitance_model")
+    out = {}
+    for method, fname, cls in (("kalman", "KalmanUpdater.py", "KalmanCapacitanceUpdater"),
+                               ("direct", "DirectUpdater.py", "DirectCapacitanceUpdater")):
+        spec = importlib.util.spec_from_file_location("ref_" + method, os.path.join(base, fname))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        for k_out in (3, 2):
+            values = rng.normal(0.0, 0.3, size=(n_step, n_env, n_dot - 1, k_out)).astype(np.float32)
+            log_vars = rng.uniform(-8.0, 0.0, size=(n_step, n_env, n_dot - 1, k_out)).astype(np.float32)
+            means = np.zeros((n_step, n_env, n_dot, n_dot))
+            variances = np.zeros_like(means)
+            full = np.zeros_like(means)
+            for e in range(n_env):
+                upd = getattr(mod, cls)(n_dots=n_dot, prior_mean=0.3, prior_variance=0.5, variance_threshold=0.05,
+                                        process_noise=0.01 if e % 2 else 0.0, include_nnn=(k_out == 3),
+                                        prior_mean_nnn=0.15)
+                for t in range(n_step):
+                    for i in range(n_dot - 1):       # the caller's loop, env.py:596-618 (values negated there)
+                        upd.update_from_scan(left_dot=i, ml_outputs=[
+                            (-float(values[t, e, i, k]), float(log_vars[t, e, i, k])) for k in range(k_out)])
+                    means[t, e], variances[t, e], full[t, e] = upd.means, upd.variances, upd.get_full_matrix()
+            tag = f"{method}_k{k_out}"
+            out.update({tag + "_values": values, tag + "_log_vars": log_vars, tag + "_means": means,
+                        tag + "_variances": variances, tag + "_full": full})
+    # VGM update, barrier mode
+    dev = synth.sample_barrier_devices(n_env, n_dot, seed=seed)
+    mb = synth.tunnel_batch(dev)
+    fn = _reference_functions(os.path.join(refshim.REF_SRC, "qadapt", "environment", "qarray_base_class.py"),
+                              ["_update_virtual_gate_matrix", "_set_vgm_for_target_effective_coupling"], {"np": np})
+    est = rng.uniform(0.0, 0.6, size=(n_env, n_dot, n_dot))
+    est = 0.5 * (est + est.transpose(0, 2, 1))
+    est[:, np.arange(n_dot), np.arange(n_dot)] = 1.0
+    target = np.broadcast_to(np.eye(n_dot), (n_env, n_dot, n_dot)).copy()
+    target[:, 0, 1] = target[:, 1, 0] = rng.uniform(-0.4, 0.4, size=n_env)
+    vgm_e, vgm_h, vgm_t = [], [], []
+    for e in range(n_env):
+        for carrier, sink in (("electrons", vgm_e), ("h", vgm_h)):
+            composer = types.SimpleNamespace(virtual_gate_matrix=None)
+            model = types.SimpleNamespace(cgd_full=mb.cgd_full[e], cdd_inv_full=mb.cdd_inv_full[e], n_gate=n_dot + 1,
+                                          charge_carrier=carrier, gate_voltage_composer=composer)
+            me = types.SimpleNamespace(use_barriers=True, model=model, num_dots=n_dot, num_barrier_voltages=n_dot - 1)
+            fn["_update_virtual_gate_matrix"](me, est[e])
+            sink.append(np.array(composer.virtual_gate_matrix))
+        fn["_set_vgm_for_target_effective_coupling"](me, target[e])          # 'h' model from the loop above
+        vgm_t.append(np.array(composer.virtual_gate_matrix))
+    out.update(cdd_inv_full=mb.cdd_inv_full, cgd_full=mb.cgd_full, cgd_estimate=est, vgm_electrons=np.stack(vgm_e),
+               vgm_holes=np.stack(vgm_h), target=target, vgm_target_holes=np.stack(vgm_t), n_dot=n_dot)
+    return out
+
+
 def main(only=None):
+    if not only or "ref_virtualisation" in only:
+        np.savez_compressed(os.path.join(HERE, "ref_virtualisation.npz"), **run_reference_virtualisation())
+        print("ref_virtualisation: kalman/direct x {3, 2} outputs, VGM update", flush=True)
     for name, spec in CASES_A.items():
         if only and name not in only:
             continue

@@ -57,10 +57,58 @@ def time_cpu(mb, scans, budget_s=3.0):
     return {"pixels_per_s": pps, "cores": cores, "sample_scans": n, "seconds": dt}
 
 
+def next_rows(eng, out, quick=False):
+    """batched env.step with CNN + Kalman virtualisation in the loop (BASELINE config 3's
+    'Kalman virtualisation in the loop'), and dataset generation, wall-clock around whole calls."""
+    import time
+    from qdsim.dataset import generate_batch
+    from qdsim.vector_env import BatchedDeviceEnv, EnvConfig
+    from qdsim.virtualisation import make_capacitance_cnn
+    torch.manual_seed(0)
+    cnn = make_capacitance_cnn(3).cuda().eval()
+    rows = {}
+    for n_dot, n_env in ((4, 1024), (6, 256 if quick else 1024)):
+        for method in (None, "kalman"):
+            env = BatchedDeviceEnv(n_env, n_dot, engine=eng, seed=1, capacitance_model=cnn if method else None,
+                                   config=EnvConfig(resolution=64, max_steps=50, update_method=method))
+            if env.vg_updater is not None:
+                env.vg_updater.autocast_dtype = torch.bfloat16
+            env.reset()
+            rng = np.random.default_rng(0)
+            acts = [(rng.uniform(-0.1, 0.1, (n_env, n_dot)), rng.uniform(-0.1, 0.1, (n_env, n_dot - 1))) for _ in range(4)]
+            env.step(*acts[0])
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for a in acts[1:]:
+                env.step(*a)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / 3
+            rows[f"{n_dot}dot_{n_env}env_64x64_tunnel_update_{method}"] = {"ms_per_step": dt * 1e3, "env_steps_per_s": n_env / dt}
+            print(n_dot, n_env, method, dt, file=sys.stderr)
+    out["batched_env_shell_virtualisation_in_loop"] = rows
+    ds = {}
+    for use_barriers, n_s in ((False, 4096), (True, 256 if quick else 1024)):
+        generate_batch(eng, 64, 4, seed=1, use_barriers=use_barriers, res=100)
+        t0 = time.perf_counter()
+        generate_batch(eng, n_s, 4, seed=2, use_barriers=use_barriers, res=100)
+        dt = time.perf_counter() - t0
+        ds[f"4dot_100x100_{'tunnel' if use_barriers else 'path_A'}"] = {"samples": n_s, "samples_per_s": n_s / dt,
+                                                                        "note": "images copied to host, reference layout"}
+    out["dataset_generation"] = ds
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--next-rows-only", action="store_true",
+                    help="only the SURVEY 8f rows: env shell with Kalman virtualisation in the loop, dataset generation")
     args = ap.parse_args()
+    if args.next_rows_only:
+        eng = Engine(0)
+        out = {"gpu": torch.cuda.get_device_name(0)}
+        next_rows(eng, out, args.quick)
+        print(json.dumps(out, indent=1))
+        return
     eng = Engine(0)
     out = {"gpu": torch.cuda.get_device_name(0), "flags": "latching + white/telegraph/radial noise, T=0"}
 
