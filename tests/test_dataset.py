@@ -60,7 +60,7 @@ def test_generate_and_save_batch(engine, tmp_path, use_barriers):
 def test_far_windows_are_replaced_by_noise(engine):
     """+-40 V offsets put most windows beyond full_noise_distance: those scans are pure N(0,1) (qarray_base_class.py:463-468)."""
     from qdsim.dataset import generate_batch
-    batch = generate_batch(engine, 16, 4, seed=9, res=32)
+    batch = generate_batch(engine, 16, 4, seed=9, res=32, voltage_offset=80.0)
     s = batch["scans"]
     far = s["rad_mode"] == 2
     assert far.mean() > 0.3
