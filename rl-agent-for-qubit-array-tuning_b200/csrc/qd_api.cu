@@ -156,7 +156,7 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
     g.n_out = nullptr; g.nbar = ctx->d_nbar; g.n_scan = n_scan; g.n_type = QD_N_NONE; g.flags = flags;
     g.slot_bytes = qd::qd_tunnel_slot_bytes(ctx->L);
     const long long max_pix = ctx->up_max_pix;
-    const long long want_items = (long long)ctx->sm_count * 8 * 4;
+    const long long want_items = (long long)ctx->sm_count * 12 * 4;
     long long ppi = ((long long)n_scan * max_pix) / want_items;          // pixels per item
     if (ppi < 1) ppi = 1;
     if (ppi > 64) ppi = 64;

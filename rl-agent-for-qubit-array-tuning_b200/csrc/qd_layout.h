@@ -37,7 +37,8 @@ struct qd_layout {
   int32_t o_sneg;    // [8]        2 * sum_{k != j} min(Cinv_jk, 0)
   int32_t o_q;       // [2^N]      Q[delta] = delta^T cdd_inv delta, delta in {0,1}^N, dot 0 = most significant bit
   int32_t o_cbg;     // [B*G]      (tunnel) raw positive barrier-gate matrix
-  int32_t o_schur, o_qhh, o_qll;   // unused (kept for ABI stability of the struct): tunnel tables live in the kernel
+  int32_t gs_doubles;   // (tunnel) length of the record PREFIX the ground-state kernel stages: cinv | a | par | alpha | cbg
+  int32_t pad0, pad1;
   int32_t rec_doubles;  // total, multiple of 2 (16 bytes)
 };
 
@@ -47,25 +48,44 @@ static inline qd_layout qd_make_layout(int n_dot, int n_volt, int n_gate, int al
   L.num_states = num_states; L.chunk = chunk;
   int o = 0;
   L.o_cinv = o;   o += n_dot * n_dot;
-  L.o_cdd = o;    o += n_dot * n_dot;
-  L.o_a = o;      o += n_dot * n_volt;
-  L.o_sw = o;     o += n_dot;
-  L.o_css = o;    o += 1;
-  L.o_sa = o;     o += n_volt;
-  L.o_par = o;    o += QD_PAR_COUNT;
-  L.o_alpha = o;  o += 8;
-  L.o_pleads = o; o += 8;
-  L.o_pinter = o; o += 64;
-  L.o_spos = o;   o += 8;
-  L.o_sneg = o;   o += 8;
-  o = (o + 1) & ~1;                       // Q rows are read as 16-byte pairs
-  L.o_q = o;
-  if (algorithm == QD_ALG_DEFAULT || algorithm == QD_ALG_THRESHOLDED) o += (1 << n_dot);
-  L.o_cbg = o;
-  if (algorithm == QD_ALG_TUNNEL) o += (n_volt - n_gate) * n_gate;
-  L.o_schur = o;
-  L.o_qhh = o;
-  L.o_qll = o;
+  if (algorithm == QD_ALG_TUNNEL) {
+    // Everything qd_tunnel_gs_kernel reads comes first, so that its warps stage a short prefix only (their shared
+    // memory also holds a 32 x 32 Hamiltonian; the smaller the slot, the more warps stay resident).
+    L.o_a = o;      o += n_dot * n_volt;
+    L.o_par = o;    o += QD_PAR_COUNT;
+    L.o_alpha = o;  o += 8;
+    L.o_cbg = o;    o += (n_volt - n_gate) * n_gate;
+    o = (o + 1) & ~1;
+    L.gs_doubles = o;
+    L.o_cdd = o;    o += n_dot * n_dot;
+    L.o_sw = o;     o += n_dot;
+    L.o_css = o;    o += 1;
+    L.o_sa = o;     o += n_volt;
+    L.o_pleads = o; o += 8;
+    L.o_pinter = o; o += 64;
+    L.o_spos = o;   o += 8;
+    L.o_sneg = o;   o += 8;
+    o = (o + 1) & ~1;
+    L.o_q = o;
+  } else {
+    L.o_cdd = o;    o += n_dot * n_dot;
+    L.o_a = o;      o += n_dot * n_volt;
+    L.o_sw = o;     o += n_dot;
+    L.o_css = o;    o += 1;
+    L.o_sa = o;     o += n_volt;
+    L.o_par = o;    o += QD_PAR_COUNT;
+    L.o_alpha = o;  o += 8;
+    L.o_pleads = o; o += 8;
+    L.o_pinter = o; o += 64;
+    L.o_spos = o;   o += 8;
+    L.o_sneg = o;   o += 8;
+    o = (o + 1) & ~1;                       // Q rows are read as 16-byte pairs
+    L.o_q = o;
+    if (algorithm == QD_ALG_DEFAULT || algorithm == QD_ALG_THRESHOLDED) o += (1 << n_dot);
+    L.o_cbg = o;
+    L.gs_doubles = 0;
+  }
+  L.pad0 = L.pad1 = 0;
   // (the tunnel path's block tables depend on a per-item permutation of the dots and are built inside the kernel)
   L.rec_doubles = (o + 1) & ~1;
   return L;

@@ -22,11 +22,11 @@
 namespace qd {
 
 constexpr int QD_T_HS = 33;                       // row stride of H in shared memory (bank-conflict free)
-constexpr int QD_T_TAB = 64 + 16 + 256 + 256 + 16;      // per-item: permuted Cinv, Schur block, Qhh, Qll, perm / inverse perm
+constexpr int QD_T_TAB = 64 + 16 + 256 + 16;      // per-item: permuted Cinv, Schur block, Qll, perm / inverse perm
 constexpr int QD_T_WORK = 32 * QD_T_HS + 9 * 32 + 64 + QD_T_TAB;   // H, dd, ee, e2, qi, ll, yy, vq | small vectors | tables
 
 __host__ __device__ inline int qd_tunnel_slot_bytes(const qd_layout& L) {
-  int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_T_WORK * 8 + 16;
+  int b = L.gs_doubles * 8 + (int)sizeof(qd_scan) + QD_T_WORK * 8 + 16;     // record PREFIX only (qd_layout.h)
   return (b + 127) & ~127;
 }
 
@@ -38,6 +38,21 @@ __device__ __forceinline__ double warp_sum(double v) {
     v += t;
   }
   return v;
+}
+// sum over the lane segment [s0, s1] that contains this lane (segments tile the warp); every lane gets its segment's sum
+__device__ __forceinline__ double seg_sum(double v, int lane, int s0, int s1, bool wide) {
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) {
+    const double t = __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), d),
+                                      __shfl_up_sync(0xffffffffu, __double2loint(v), d));
+    if (lane - d >= s0) v += t;
+  }
+  if (wide) {                                      // segments longer than 16 lanes (warp-uniform flag)
+    const double t = __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(v), 16),
+                                      __shfl_up_sync(0xffffffffu, __double2loint(v), 16));
+    if (lane - 16 >= s0) v += t;
+  }
+  return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), s1), __shfl_sync(0xffffffffu, __double2loint(v), s1));
 }
 __device__ __forceinline__ double warp_min(double v) {
 #pragma unroll
@@ -89,8 +104,8 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
 
   unsigned char* slot = qd_smem + (size_t)warp * a.slot_bytes;
   double* rec = reinterpret_cast<double*>(slot);
-  qd_scan* sc = reinterpret_cast<qd_scan*>(slot + (size_t)L.rec_doubles * 8);
-  double* wk = reinterpret_cast<double*>(slot + (size_t)L.rec_doubles * 8 + sizeof(qd_scan));
+  qd_scan* sc = reinterpret_cast<qd_scan*>(slot + (size_t)L.gs_doubles * 8);
+  double* wk = reinterpret_cast<double*>(slot + (size_t)L.gs_doubles * 8 + sizeof(qd_scan));
   double* H = wk;
   double* dd = wk + 32 * QD_T_HS;
   double* ee = dd + 32;
@@ -109,8 +124,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
   double* nb = sv + 56;
   double* Cp = sv + 64;          // Cinv with rows / columns permuted so that the stiffest dots come first
   double* Sp = Cp + 64;          // Schur complement of the permuted high block
-  double* Qh = Sp + 16;          // x^T Cp_hh x over the high digit combinations
-  double* Ql = Qh + 256;         // y^T Cp_ll y over the low digit combinations
+  double* Ql = Sp + 16;          // y^T Cp_ll y over the low digit combinations
   int* pm = reinterpret_cast<int*>(Ql + 256);   // pm[j]: dot at permuted position j;  pm[8 + d]: position of dot d
   uint64_t* bar = reinterpret_cast<uint64_t*>(wk + QD_T_WORK);
 
@@ -120,7 +134,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
   uint32_t phase = 0;
-  const uint32_t rec_bytes = (uint32_t)L.rec_doubles * 8u;
+  const uint32_t rec_bytes = (uint32_t)L.gs_doubles * 8u;
 
   const long long total_items = (long long)a.n_scan * a.items_per_scan;
   for (long long item = (long long)blockIdx.x * warps_per_cta + warp; item < total_items;
@@ -201,13 +215,6 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               for (int q = 0; q < NLO; ++q) acc -= Cp[i * N + NHI + p] * m[p][NLO + q] * Cp[(NHI + q) * N + j];
             Sp[i * NHI + j] = acc;
           }
-      }
-      for (int idx = lane; idx < NB_HI; idx += 32) {
-        double acc = 0.0;
-        for (int i = 0; i < NHI; ++i)
-          for (int j = 0; j < NHI; ++j)
-            acc += (double)(((idx >> (2 * (NHI - 1 - i))) & 3) - 1) * Cp[i * N + j] * (double)(((idx >> (2 * (NHI - 1 - j))) & 3) - 1);
-        Qh[idx] = acc;
       }
       for (int idx = lane; idx < NB_LO; idx += 32) {
         double acc = 0.0;
@@ -359,16 +366,22 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
             for (int i = 0; i < HI_IT; ++i)
               if (mb == i * 32 + lane) lb[i] = INF;
             // block constants: base = E0 + 2 x.h_hi + Qhh[x];  c_k = 2 (h_lo[k] + sum_j C[lo k][hi j] x_j)
-            double base = E0 + Qh[mb];
+            double base = E0;
             double c[NLO];
 #pragma unroll
             for (int k = 0; k < NLO; ++k) c[k] = h[NHI + k];
+            double xh[NHI > 0 ? NHI : 1];
+#pragma unroll
+            for (int j = 0; j < NHI; ++j) xh[j] = (double)(((mb >> (2 * (NHI - 1 - j))) & 3) - 1);
 #pragma unroll
             for (int j = 0; j < NHI; ++j) {
-              const double xj = (double)(((mb >> (2 * (NHI - 1 - j))) & 3) - 1);
-              base = fma(2.0 * xj, h[j], base);
+              // x^T Cp_hh x (symmetric: diagonal + twice the strict upper part) + 2 x.h_hi
+              double s = fma(Cp[j * N + j], xh[j], 2.0 * h[j]);
 #pragma unroll
-              for (int k = 0; k < NLO; ++k) c[k] = fma(Cp[(NHI + k) * N + j], xj, c[k]);
+              for (int q = j + 1; q < NHI; ++q) s = fma(2.0 * Cp[j * N + q], xh[q], s);
+              base = fma(xh[j], s, base);
+#pragma unroll
+              for (int k = 0; k < NLO; ++k) c[k] = fma(Cp[(NHI + k) * N + j], xh[j], c[k]);
             }
 #pragma unroll 1
             for (int i = 0; i < LO_IT; ++i) {
@@ -406,11 +419,14 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           // ---------------- 3. basis states, free energies, Hamiltonian ----------------
           double st[N];
           uint64_t key = 0;
+          int tc = 0;                                // total charge of this lane's state
 #pragma unroll
           for (int j = 0; j < N; ++j) {
             // dot j sits at permuted position pm[8 + j]: its digit is read there
-            st[j] = (lidx < 0) ? 0.0 : fs[j] + (double)(((lidx >> (2 * (N - 1 - pm[8 + j]))) & 3) - 1);
-            key |= (uint64_t)((unsigned)(int)st[j] & 0xffu) << (8 * j);
+            const int sj = (lidx < 0) ? 0 : (int)fs[j] + (((lidx >> (2 * (N - 1 - pm[8 + j]))) & 3) - 1);
+            st[j] = (double)sj;
+            tc += sj;
+            key |= (uint64_t)((unsigned)sj & 0xffu) << (8 * j);
           }
           double Fm = 0.0;
           {
@@ -425,10 +441,45 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               Fm = fma(zz[i], s, Fm);
             }
           }
-          // Row `lane` of H.  Two states are connected by a hop iff they differ in exactly two ADJACENT dots, by
-          // (-1, +1) or (+1, -1): test on the XOR of the packed states first (cheap reject), then compare the byte pair.
+          // Hopping conserves the total charge, so H is block diagonal once the basis is ordered by total charge: the
+          // 32 kept states typically fall into 5-6 sectors of <= 10-16 states.  Sort the lanes by (total charge, lane)
+          // -- the spectrum and the weights |psi_m|^2 do not depend on the order of the basis -- and run every dense
+          // step below on all sectors AT ONCE, each in its own lane segment [s0, s1]: reductions are segmented, the
+          // inner loops run over the sector's columns only, and the number of Householder steps is the largest sector
+          // size minus two instead of 30.
+          int s0, s1, maxlen;
+          {
+            const unsigned same = __match_any_sync(0xffffffffu, tc);
+            int rank = __popc(same & ((1u << lane) - 1u));
+            unsigned rem = 0xffffffffu;
+            while (rem) {
+              const int leader = __ffs(rem) - 1;
+              const int v = __shfl_sync(0xffffffffu, tc, leader);
+              const unsigned grp = __shfl_sync(0xffffffffu, same, leader);
+              if (v < tc) rank += __popc(grp);
+              rem &= ~grp;
+            }
+            int* perm = reinterpret_cast<int*>(vq);
+            perm[rank] = lane;
+            __syncwarp();
+            const int src = perm[lane];
+            __syncwarp();
+            key = shfl_u64(key, src);
+            Fm = shfl_f64(Fm, src);
+            tc = __shfl_sync(0xffffffffu, tc, src);
+#pragma unroll
+            for (int j = 0; j < N; ++j) st[j] = (double)(int)(signed char)(unsigned char)(key >> (8 * j));
+            const unsigned seg = __match_any_sync(0xffffffffu, tc);
+            s0 = __ffs(seg) - 1;
+            s1 = 31 - __clz(seg);
+            maxlen = __reduce_max_sync(0xffffffffu, s1 - s0 + 1);
+          }
+          // Row `lane` of H, columns of its own sector only.  Two states are connected by a hop iff they differ in
+          // exactly two ADJACENT dots, by (-1, +1) or (+1, -1): test on the XOR of the packed states first (cheap
+          // reject), then compare the byte pair.
 #pragma unroll 1
-          for (int j = 0; j < 32; ++j) {
+          for (int u = 0; u < maxlen; ++u) {
+            const int j = min(s0 + u, 31);
             const uint64_t kj = shfl_u64(key, j);
             double val = (j == lane) ? Fm : 0.0;
             const uint64_t Hm = 0x8080808080808080ULL;
@@ -441,93 +492,106 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               if (pb == pa + 0xffu) val = -ts[p0] * (sq_tab[a0] * sq_tab[a1 + 1]);        // p0 -> p0+1
               else if (pb + 0xffu == pa) val = -ts[p0] * (sq_tab[a1] * sq_tab[a0 + 1]);   // p0+1 -> p0
             }
-            H[lane * QD_T_HS + j] = val;
+            if (s0 + u <= s1) H[lane * QD_T_HS + j] = val;
           }
           __syncwarp();
 
           // ---------------- 4. ground eigenvector ----------------
-          for (int k = 0; k < 30; ++k) {
-            const double x = (lane > k) ? H[lane * QD_T_HS + k] : 0.0;
-            const double xk1 = shfl_f64(x, k + 1);
-            const double sig = warp_sum((lane > k + 1) ? x * x : 0.0);
-            if (sig == 0.0) {
-              if (lane == 0) ee[k] = xk1;
-              if (lane > k) H[lane * QD_T_HS + k] = 0.0;
-              __syncwarp();
-              continue;
+          // Householder tridiagonalisation of every sector at once: step t works on column k = s0 + t of each sector
+          // that still has at least two rows below it.
+          const bool wide = maxlen > 16;
+          for (int t = 0; t + 2 < maxlen; ++t) {
+            const int k = s0 + t;
+            const bool act = k + 2 <= s1;
+            const double x = (act && lane > k) ? H[lane * QD_T_HS + k] : 0.0;
+            const double xk1 = shfl_f64(x, min(k + 1, 31));
+            const double sig = seg_sum((lane > k + 1) ? x * x : 0.0, lane, s0, s1, wide);
+            const bool refl = act && sig != 0.0;
+            double v = 0.0, alpha = xk1;
+            if (refl) {
+              const double norm2 = sig + xk1 * xk1;
+              alpha = (xk1 > 0.0) ? -sqrt(norm2) : sqrt(norm2);
+              v = x;
+              if (lane == k + 1) v -= alpha;
+              v *= rsqrt(2.0 * (norm2 - alpha * xk1));
             }
-            const double norm2 = sig + xk1 * xk1;
-            const double alpha = (xk1 > 0.0) ? -sqrt(norm2) : sqrt(norm2);
-            double v = x;
-            if (lane == k + 1) v -= alpha;
-            const double vn2 = 2.0 * (norm2 - alpha * xk1);
-            v *= rsqrt(vn2);
             vq[2 * lane] = v;
             __syncwarp();
             double p = 0.0;
-            if (lane > k) {
+            if (refl && lane > k) {
               double p0 = 0.0, p1 = 0.0;
               const double* __restrict__ hrow = H + lane * QD_T_HS;
               int j = k + 1;
-              for (; j + 1 < 32; j += 2) {
+              for (; j + 1 <= s1; j += 2) {
                 p0 = fma(hrow[j], vq[2 * j], p0);
                 p1 = fma(hrow[j + 1], vq[2 * j + 2], p1);
               }
-              if (j < 32) p0 = fma(hrow[j], vq[2 * j], p0);
+              if (j <= s1) p0 = fma(hrow[j], vq[2 * j], p0);
               p = p0 + p1;
             }
-            const double K = warp_sum(v * p);
+            const double K = seg_sum(v * p, lane, s0, s1, wide);
             const double q = p - K * v;
             vq[2 * lane + 1] = q;
             __syncwarp();
-            if (lane > k) {
-              const double v2 = -2.0 * v, q2 = -2.0 * q;
+            if (act && lane > k) {
               double* __restrict__ hrow = H + lane * QD_T_HS;
-              for (int j = k + 1; j < 32; ++j) {
-                const double2 o = *reinterpret_cast<const double2*>(vq + 2 * j);     // (v_j, q_j)
-                hrow[j] = fma(v2, o.y, fma(q2, o.x, hrow[j]));
+              if (refl) {
+                const double v2 = -2.0 * v, q2 = -2.0 * q;
+                for (int j = k + 1; j <= s1; ++j) {
+                  const double2 o = *reinterpret_cast<const double2*>(vq + 2 * j);     // (v_j, q_j)
+                  hrow[j] = fma(v2, o.y, fma(q2, o.x, hrow[j]));
+                }
               }
-              hrow[k] = v;                                     // the dead column keeps the reflector
+              hrow[k] = v;                                     // the dead column keeps the reflector (0: none)
             }
-            if (lane == 0) ee[k] = alpha;
+            if (act && lane == s0) ee[k] = alpha;
             __syncwarp();
           }
           dd[lane] = H[lane * QD_T_HS + lane];
-          if (lane == 0) { ee[30] = H[31 * QD_T_HS + 30]; ee[31] = 0.0; }
+          // last coupling inside each sector, and none across sectors
+          if (lane == s1) ee[lane] = 0.0;
+          else if (lane == s1 - 1) ee[lane] = H[s1 * QD_T_HS + lane];
           __syncwarp();
-          e2[lane] = ee[lane] * ee[lane];
           double lo, hi;
           {
             const double rad = ((lane > 0) ? fabs(ee[lane - 1]) : 0.0) + ((lane < 31) ? fabs(ee[lane]) : 0.0);
             lo = warp_min(dd[lane] - rad);
             hi = warp_max(dd[lane] + rad);
           }
+          // Lowest eigenvalue by 32-way multisection.  x < lambda_0  <=>  T - x I positive definite  <=>  every leading
+          // principal minor p_i(x) > 0 (Sylvester); the minors obey p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1}.  The
+          // tridiagonal is mapped onto [0, 1] first (Gershgorin interval), so |d - x| <= 1, e^2 <= 1 and the minors
+          // cannot overflow; a positive rescale every 8 steps guards the underflow side.
+          const double lo0 = lo, wid = fmax(hi - lo, 1e-300), iw = 1.0 / wid;
+          qi[lane] = (dd[lane] - lo0) * iw;
+          e2[lane] = (ee[lane] * iw) * (ee[lane] * iw);
           __syncwarp();
-          for (int round = 0; round < 7; ++round) {
+          lo = 0.0;
+          hi = 1.0;
+          for (int round = 0; round < 6; ++round) {
             const double x = fma((double)(lane + 1) * (1.0 / 33.0), hi - lo, lo);
-            // Sturm count in product form p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1} (no division); the count is the
-            // number of sign changes, an exact zero inheriting the sign of its predecessor; rescaled against overflow.
-            double pp = 1.0, pc = dd[0] - x;
-            bool neg = pc < 0.0;
-            int cnt = neg;
-            for (int i = 1; i < 32; ++i) {
-              double pn = fma(dd[i] - x, pc, -e2[i - 1] * pp);
-              const bool nneg = (pn < 0.0) || (pn == 0.0 && neg);
-              cnt += nneg != neg;
-              neg = nneg;
-              const double an = fabs(pn);
-              if (an > 1e100) { pn *= 1e-100; pc *= 1e-100; }
-              else if (an < 1e-100 && an > 0.0) { pn *= 1e100; pc *= 1e100; }
-              pp = pc;
-              pc = pn;
+            double pp = 1.0, pc = qi[0] - x;
+            bool below = !(pc > 0.0);                  // some eigenvalue lies at or below x
+#pragma unroll
+            for (int i0 = 1; i0 < 32; i0 += 8) {
+#pragma unroll
+              for (int i = i0; i < i0 + 8 && i < 32; ++i) {
+                const double pn = fma(qi[i] - x, pc, -e2[i - 1] * pp);
+                below |= !(pn > 0.0);
+                pp = pc;
+                pc = pn;
+              }
+              if (pc < 1e-150) { pc *= 1e150; pp *= 1e150; }      // (irrelevant once `below` is set)
             }
-            const unsigned mm = __ballot_sync(0xffffffffu, cnt >= 1);
+            const unsigned mm = __ballot_sync(0xffffffffu, below);
             const int j = mm ? __ffs(mm) - 1 : 32;
             const double xl = shfl_f64(x, (j > 0) ? j - 1 : 0);
             const double xh = shfl_f64(x, (j < 32) ? j : 31);
             if (j > 0) lo = xl;
             if (j < 32) hi = xh;
           }
+          lo = fma(lo, wid, lo0);
+          __syncwarp();
           const double mu = lo;
           if (lane == 0) {
             double q = dd[0] - mu;
@@ -562,9 +626,10 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
             __syncwarp();
           }
           double psi = yy[lane];
-          for (int k = 29; k >= 0; --k) {
-            const double v = (lane > k) ? H[lane * QD_T_HS + k] : 0.0;
-            const double dot = warp_sum(v * psi);
+          for (int t = maxlen - 3; t >= 0; --t) {
+            const int k = s0 + t;
+            const double v = (k + 2 <= s1 && lane > k) ? H[lane * QD_T_HS + k] : 0.0;
+            const double dot = seg_sum(v * psi, lane, s0, s1, wide);
             psi = fma(-2.0 * dot, v, psi);
           }
           {

@@ -3,6 +3,7 @@
 its "owner"; another object re-uploads its own constants first (a few KB)."""
 from __future__ import annotations
 
+import itertools
 import os
 
 import numpy as np
@@ -10,7 +11,8 @@ import numpy as np
 from .engine import Engine
 
 _engines: dict[int, Engine] = {}
-_owner: dict[int, int] = {}
+_owner: dict[int, tuple] = {}
+_tokens = itertools.count(1)
 
 
 def default_device() -> int:
@@ -23,7 +25,11 @@ def engine_for(model, device: int | None = None) -> Engine:
     eng = _engines.get(dev)
     if eng is None:
         eng = _engines[dev] = Engine(dev)
-    key = (id(model), model._version)
+    token = model.__dict__.get("_qd_token")
+    if token is None:                    # never id(model): the address of a collected model is reused by the next one
+        token = next(_tokens)
+        object.__setattr__(model, "_qd_token", token)
+    key = (token, model._version)
     if _owner.get(dev) != key:
         eng.set_models(model._model_batch())
         _owner[dev] = key
