@@ -260,30 +260,34 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           }
           __syncwarp();
           // ---------------- continuous relaxation (charge_states.py:36-88) ----------------
+          // Lane (4 i + p) works for dot i on the columns k = 2p, 2p + 1 of C: a projected-gradient step is two
+          // products, a 4-lane butterfly and the update, all in registers (no shared-memory round trip per step).
           {
-            const double gj = (lane < N) ? gs[lane] : 0.0;
-            double nj = gj;
-            if (__ballot_sync(0xffffffffu, lane < N && gj < 0.0)) {
-              double cg = 0.0;
-              if (lane < N)
-                for (int k = 0; k < N; ++k) cg = fma(C[lane * N + k], gs[k], cg);
-              nj = fmax(gj, 0.0);
+            const int di = lane >> 2, dp = lane & 3;
+            const int k0 = 2 * dp, k1 = 2 * dp + 1;
+            const bool own = di < N;
+            const double gi = own ? gs[di] : 0.0;
+            double ni = gi;
+            if (__ballot_sync(0xffffffffu, own && gi < 0.0)) {
+              const double c0 = (own && k0 < N) ? C[di * N + k0] : 0.0;
+              const double c1 = (own && k1 < N) ? C[di * N + k1] : 0.0;
+              const int l0 = (k0 < N) ? 4 * k0 : lane, l1 = (k1 < N) ? 4 * k1 : lane;   // lanes holding n_k0, n_k1
+              double cg = fma(c0, (k0 < N) ? gs[k0] : 0.0, c1 * ((k1 < N) ? gs[k1] : 0.0));
+              cg += shfl_f64(cg, lane ^ 1);
+              cg += shfl_f64(cg, lane ^ 2);
+              ni = fmax(gi, 0.0);
               for (int it = 0; it < 50; ++it) {
-                if (lane < N) ns[lane] = nj;
-                __syncwarp();
-                if (lane < N) {
-                  double grad = 0.0;
-                  for (int k = 0; k < N; ++k) grad = fma(C[lane * N + k], ns[k], grad);
-                  nj = fmax(nj - 0.1 * (grad - cg), 0.0);
-                }
-                __syncwarp();
+                double part = fma(c0, shfl_f64(ni, l0), c1 * shfl_f64(ni, l1));
+                part += shfl_f64(part, lane ^ 1);
+                part += shfl_f64(part, lane ^ 2);
+                ni = fmax(ni - 0.1 * (part - cg), 0.0);
               }
             }
-            nj = fmax(nj, 0.0);
-            if (lane < N) {
-              const double fj = floor(nj);
-              fs[lane] = fj;
-              ns[lane] = fj - gj;                    // r = f - g
+            ni = fmax(ni, 0.0);
+            if (own && dp == 0) {
+              const double fj = floor(ni);
+              fs[di] = fj;
+              ns[di] = fj - gi;                      // r = f - g
             }
           }
           __syncwarp();
@@ -593,9 +597,11 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           lo = fma(lo, wid, lo0);
           __syncwarp();
           const double mu = lo;
-          if (lane == 0) {
-            double q = dd[0] - mu;
-            for (int i = 0; i < 31; ++i) {
+          // LDL^T of T - mu I and the inverse-iteration solves, every sector by its own leader lane (the sectors are
+          // decoupled: ee[s1] = 0), so the serial chains are one sector long instead of 32.
+          if (lane == s0) {
+            double q = dd[s0] - mu;
+            for (int i = s0; i < s1; ++i) {
               if (!(q > 0.0)) q = 1e-300;
               const double iq = 1.0 / q;
               qi[i] = iq;
@@ -604,17 +610,17 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               q = (dd[i + 1] - mu) - l * ee[i];
             }
             if (!(q > 0.0)) q = 1e-300;
-            qi[31] = 1.0 / q;
+            qi[s1] = 1.0 / q;
           }
           yy[lane] = 1.0 + (double)lane * (1.0 / 64.0);
           __syncwarp();
           for (int it = 0; it < 3; ++it) {
-            if (lane == 0) {
-              double zprev = yy[0];
-              for (int i = 1; i < 32; ++i) { zprev = yy[i] - ll[i - 1] * zprev; yy[i] = zprev; }
-              double ynext = yy[31] * qi[31];
-              yy[31] = ynext;
-              for (int i = 30; i >= 0; --i) { ynext = yy[i] * qi[i] - ll[i] * ynext; yy[i] = ynext; }
+            if (lane == s0) {
+              double zprev = yy[s0];
+              for (int i = s0 + 1; i <= s1; ++i) { zprev = yy[i] - ll[i - 1] * zprev; yy[i] = zprev; }
+              double ynext = yy[s1] * qi[s1];
+              yy[s1] = ynext;
+              for (int i = s1 - 1; i >= s0; --i) { ynext = yy[i] * qi[i] - ll[i] * ynext; yy[i] = ynext; }
             }
             __syncwarp();
             double yv = yy[lane];
