@@ -175,6 +175,47 @@ def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int, pat
     return dev, mb, sets
 
 
+def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_env: int = 512):
+    """Path B on the same GPU: n_env envs of the n_dot tunnel-coupled array, device-resident, CUDA events; the NumPy
+    restatement (pinned against the reference itself, tests/test_reference_golden.py) timed on a small sample."""
+    import torch
+    from qdsim import N_F32
+    dev, mb, sets = build_workload(n_env, n_dot, res, 0, 1, "B")
+    eng.set_models(mb)
+    scans = sets[0]
+    pixels = len(scans) * res * res
+    st = torch.cuda.current_stream()
+    z = torch.empty(pixels, dtype=torch.float32, device="cuda")
+    n = torch.empty((pixels, n_dot), dtype=torch.float32, device="cuda")
+    eng.scan_upload(scans, st)
+    eng.scan_launch(z, n, N_F32, flags, st)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 2
+    e0.record(st)
+    for _ in range(steps):
+        eng.scan_launch(z, n, N_F32, flags, st)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    blk = {"workload": f"{n_dot}-dot tunnel-coupled array (TunnelCoupledChargeSensed, 32-state basis, barrier voltages), "
+                       f"{n_env} envs, {n_dot - 1} scans/env of {res}x{res}, latching + noise",
+           "kernels": f"qd_tunnel_gs_kernel<{n_dot}> + qd_scan_kernel<{n_dot},tunnel>",
+           "value": pixels / (ms * 1e-3), "unit": "pixels/s", "env_steps_per_s": n_env / (ms * 1e-3),
+           "ms_per_step": ms, "steps": steps, "cpu_baseline": None}
+    if with_cpu:
+        from util import oracle_batch
+        small = scans[:1].copy()
+        small["nx"], small["ny"] = 16, 8                    # 128 pixels of the first window (same origin and pitch)
+        t0 = time.perf_counter()
+        oracle_batch(mb, small, flags)
+        dt = time.perf_counter() - t0
+        blk["cpu_baseline"] = {"value": 128 / dt, "unit": "pixels/s", "cores": 1, "kind": "port",
+                               "sample": f"128 pixels of one scan window, {dt:.1f} s",
+                               "what": "NumPy restatement of qarray_latched._ground_state_open (vectorised over pixels)"}
+    return blk
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -186,6 +227,7 @@ def main():
     ap.add_argument("--res", type=int, default=64)
     ap.add_argument("--cpu-scans", type=int, default=0, help="scans in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-path-b", action="store_true", help="skip the secondary tunnel-coupled measurement")
     ap.add_argument("--path", default="A", choices=["A", "B"],
                     help="A: constant-interaction ChargeSensedDotArray path (headline); B: tunnel-coupled path of "
                          "env.step in barrier mode (secondary; use e.g. --n-dot 4 --n-env 1024)")
@@ -376,6 +418,9 @@ def main():
                     "h2d_bytes_per_step": int(sets[0].nbytes), "d2h_bytes_per_step": int(pixels * 4)},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum,
         }
+    # ---- (4) secondary: the tunnel-coupled path that QADAPT's env.step executes in barrier mode (Path B) ----
+    if rank == 0 and world == 1 and args.path == "A" and not args.no_path_b:
+        out["env_step_tunnel_path"] = tunnel_path_block(eng, N, res, flags, not args.no_cpu_baseline)
     # the one collective of the design, OFF the step path: per-env episode statistics to every rank (NCCL all-gather)
     if world > 1:
         from qdsim import parallel

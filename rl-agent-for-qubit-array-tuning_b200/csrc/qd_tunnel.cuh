@@ -81,6 +81,52 @@ __device__ __forceinline__ void warp_lex_max(double e, int idx, int lane, double
   }
 }
 
+// Energy of the low candidate b = 32 i + lane_b inside a block with constants (base, c):  the digits of b split into
+// bits taken from lane_b and bits taken from i.  Written once so that the streaming pass (which hoists the lane part
+// out of its loop) and the warm start evaluate a candidate with the very same operations.
+template <int NLO>
+__device__ __forceinline__ double tunnel_lane_part(double base, const double (&c)[NLO], int lane_b) {
+#pragma unroll
+  for (int k = 0; k < NLO; ++k) {
+    const int sh = 2 * (NLO - 1 - k);
+    const int dg = (sh >= 5) ? 0 : ((lane_b >> sh) & 3 & ((sh == 4) ? 1 : 3));
+    base = fma(2.0 * c[k], (double)(dg - 1), base);
+  }
+  return base;
+}
+template <int NLO>
+__device__ __forceinline__ double tunnel_iter_part(double e, const double (&c)[NLO], int i) {
+#pragma unroll
+  for (int k = 0; k < NLO; ++k) {
+    const int sh = 2 * (NLO - 1 - k);              // bit position of digit k inside b
+    if (sh + 2 > 5) {                               // (part of) the digit comes from i
+      const int di = (sh >= 5) ? ((i >> (sh - 5)) & 3) : ((i << (5 - sh)) & 3);
+      e = fma(2.0 * c[k], (double)di, e);
+    }
+  }
+  return e;
+}
+// block constants: base = E0 + 2 x.h_hi + x^T Cp_hh x;  c_k = h_lo[k] + sum_j Cp[lo k][hi j] x_j   (x = high deltas)
+template <int N, int NHI, int NLO>
+__device__ __forceinline__ void tunnel_block_constants(int mb, double E0, const double (&h)[N],
+                                                       const double* __restrict__ Cp, double& base, double (&c)[NLO]) {
+  base = E0;
+#pragma unroll
+  for (int k = 0; k < NLO; ++k) c[k] = h[NHI + k];
+  double xh[NHI > 0 ? NHI : 1];
+#pragma unroll
+  for (int j = 0; j < NHI; ++j) xh[j] = (double)(((mb >> (2 * (NHI - 1 - j))) & 3) - 1);
+#pragma unroll
+  for (int j = 0; j < NHI; ++j) {
+    double s = fma(Cp[j * N + j], xh[j], 2.0 * h[j]);          // symmetric: diagonal + twice the strict upper part
+#pragma unroll
+    for (int q = j + 1; q < NHI; ++q) s = fma(2.0 * Cp[j * N + q], xh[q], s);
+    base = fma(xh[j], s, base);
+#pragma unroll
+    for (int k = 0; k < NLO; ++k) c[k] = fma(Cp[(NHI + k) * N + j], xh[j], c[k]);
+  }
+}
+
 template <int N>
 __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
   constexpr int NLO = N < 4 ? N : 4;
@@ -229,6 +275,8 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
 
     {
       {
+        uint64_t prev_key = ~0ULL;       // this lane's basis state at the previous pixel of the item (~0: none / padding)
+        bool have_prev = false;
         for (long long pix = p_begin; pix < p_end; ++pix) {
         const int iy = (int)(pix / nx), ix = (int)(pix - (long long)iy * nx);
         double nbar[N];
@@ -310,6 +358,43 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           int lidx = -1;                             // -1: the reference's zero-state padding entry
           double tau = INF;
           int tau_idx = 0x7fffffff;
+          // Warm start.  Neighbouring pixels keep almost the same 32 states: re-evaluate the previous pixel's basis at
+          // this pixel (each lane its own state, with the streaming pass's own arithmetic), sort it, and let it be the
+          // initial list.  The pass below then only inserts the few newcomers -- the final list is the exact
+          // (energy, index) top-32 either way, the warm start only spares ~70 insertions per pixel.
+          if (have_prev) {
+            bool okp = prev_key != ~0ULL;
+            int idx = 0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              const int dg = (int)(signed char)(unsigned char)(prev_key >> (8 * j)) - (int)fs[j] + 1;
+              okp = okp && dg >= 0 && dg <= 3;
+              idx |= (dg & 3) << (2 * (N - 1 - pm[8 + j]));
+            }
+            if (okp) {
+              double base;
+              double c[NLO];
+              const int b = idx & (NB_LO - 1);
+              tunnel_block_constants<N, NHI, NLO>(idx >> (2 * NLO), E0, h, Cp, base, c);
+              le = tunnel_iter_part<NLO>(tunnel_lane_part<NLO>(base, c, b & 31) + Ql[b], c, b >> 5);
+              lidx = idx;
+            }
+            // bitonic sort of the 32 (energy, index) pairs across the lanes, ascending; padding (inf, -1) goes last
+#pragma unroll
+            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+              for (int j = k >> 1; j > 0; j >>= 1) {
+                const double oe = shfl_f64(le, lane ^ j);
+                const int oi = __shfl_xor_sync(0xffffffffu, lidx, j);
+                const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+                const bool take = keep_min ? lex_less(oe, oi, le, lidx) : lex_less(le, lidx, oe, oi);
+                if (take) { le = oe; lidx = oi; }
+              }
+            }
+            tau = shfl_f64(le, 31);
+            tau_idx = __shfl_sync(0xffffffffu, lidx, 31);
+            if (!(tau < INF)) tau_idx = 0x7fffffff;
+          }
           // validity of this lane's low candidates and their digit vectors do not depend on the block
           unsigned lo_valid = 0;
 #pragma unroll
@@ -369,33 +454,20 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
 #pragma unroll
             for (int i = 0; i < HI_IT; ++i)
               if (mb == i * 32 + lane) lb[i] = INF;
-            // block constants: base = E0 + 2 x.h_hi + Qhh[x];  c_k = 2 (h_lo[k] + sum_j C[lo k][hi j] x_j)
-            double base = E0;
+            double base;
             double c[NLO];
-#pragma unroll
-            for (int k = 0; k < NLO; ++k) c[k] = h[NHI + k];
-            double xh[NHI > 0 ? NHI : 1];
-#pragma unroll
-            for (int j = 0; j < NHI; ++j) xh[j] = (double)(((mb >> (2 * (NHI - 1 - j))) & 3) - 1);
-#pragma unroll
-            for (int j = 0; j < NHI; ++j) {
-              // x^T Cp_hh x (symmetric: diagonal + twice the strict upper part) + 2 x.h_hi
-              double s = fma(Cp[j * N + j], xh[j], 2.0 * h[j]);
-#pragma unroll
-              for (int q = j + 1; q < NHI; ++q) s = fma(2.0 * Cp[j * N + q], xh[q], s);
-              base = fma(xh[j], s, base);
-#pragma unroll
-              for (int k = 0; k < NLO; ++k) c[k] = fma(Cp[(NHI + k) * N + j], xh[j], c[k]);
-            }
+            tunnel_block_constants<N, NHI, NLO>(mb, E0, h, Cp, base, c);
+            const double base_lane = tunnel_lane_part<NLO>(base, c, lane);      // lane part, once per block
 #pragma unroll 1
-            for (int i = 0; i < LO_IT; ++i) {
+            for (int ii = 0; ii < LO_IT; ++ii) {
+              // start with the leading low digit at delta 0 / +1 (the candidates around the continuous minimum), so
+              // that the running 32nd-best energy tightens early and the far candidates never enter the list
+              const int i = (LO_IT >= 4) ? ((ii + LO_IT / 4) & (LO_IT - 1)) : ii;
               const int b = i * 32 + lane;
               const bool ok = (lo_valid >> i) & 1u;
               double e = INF;
               if (ok) {
-                e = base + Ql[b];
-#pragma unroll
-                for (int k = 0; k < NLO; ++k) e = fma(2.0 * (double)(((b >> (2 * (NLO - 1 - k))) & 3) - 1), c[k], e);
+                e = tunnel_iter_part<NLO>(base_lane + Ql[b], c, i);
               }
               const int cidx = mb * NB_LO + b;
               unsigned pm = __ballot_sync(0xffffffffu, ok && lex_less(e, cidx, tau, tau_idx));
@@ -405,6 +477,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
                 const double pe = shfl_f64(e, p);
                 const int pi = __shfl_sync(0xffffffffu, cidx, p);
                 if (lex_less(pe, pi, tau, tau_idx)) {
+                  if (have_prev && __any_sync(0xffffffffu, lidx == pi)) continue;     // already there (warm start)
                   // sorted insert: entries not below the newcomer move one lane up, the last one drops out
                   const unsigned below = __ballot_sync(0xffffffffu, lex_less(le, lidx, pe, pi));
                   const int pos = __popc(below);
@@ -415,6 +488,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
                   tau = shfl_f64(le, 31);
                   tau_idx = __shfl_sync(0xffffffffu, lidx, 31);
                   if (!(tau < INF)) tau_idx = 0x7fffffff;      // padding entries lose against every real candidate
+                  pm &= __ballot_sync(0xffffffffu, lex_less(e, cidx, tau, tau_idx));   // drop the ones now out of reach
                 }
               }
             }
@@ -471,6 +545,8 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
             key = shfl_u64(key, src);
             Fm = shfl_f64(Fm, src);
             tc = __shfl_sync(0xffffffffu, tc, src);
+            prev_key = __shfl_sync(0xffffffffu, (int)(lidx < 0), src) ? ~0ULL : key;     // warm start of the next pixel
+            have_prev = true;
 #pragma unroll
             for (int j = 0; j < N; ++j) st[j] = (double)(int)(signed char)(unsigned char)(key >> (8 * j));
             const unsigned seg = __match_any_sync(0xffffffffu, tc);
