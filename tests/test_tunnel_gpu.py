@@ -92,3 +92,42 @@ def test_tunnel_constant_tc_without_barriers(engine):
     ok = gap.reshape(-1) > 1e-4
     assert np.abs(n[ok] - np.rint(n[ok])).max() < 1e-6, "t -> 0: occupations are integers away from degeneracies"
     np.testing.assert_allclose(n[ok], n_ref.reshape(-1, 4)[ok], rtol=0, atol=N_ATOL)
+
+
+@pytest.mark.parametrize("n_dot", [6, 8])
+def test_tunnel_one_wide_sector(engine, n_dot):
+    """A stiff common mode (adding a carrier costs far more than moving one): all 32 kept states share one total charge,
+    i.e. ONE sector of 32 lanes -- the widest case of the segmented solver (segments longer than 16 lanes)."""
+    from qdsim import N_F64
+    from qdsim.engine import ModelBatch, PARAMS_DTYPE, new_scans
+    n, d = n_dot, n_dot + 1
+    rng = np.random.default_rng(70 + n_dot)
+    a = np.diag(rng.uniform(0.04, 0.07, size=d))
+    cinv_full = (a + 1.5 * np.ones((d, d)))[None]
+    cgd_full = -np.concatenate([np.eye(d) + 0.02 * rng.uniform(size=(d, d)), 0.01 * rng.uniform(size=(d, n - 1))], axis=1)[None]
+    params = np.zeros(1, dtype=PARAMS_DTYPE)
+    params["tc_base"] = 0.03
+    params["alpha"][0, :n - 1] = 1.0
+    mb = ModelBatch(algorithm="tunnel", n_gate=d, cdd_inv_gs=np.ascontiguousarray(cinv_full[:, :n, :n]), cdd_gs=None,
+                    cdd_inv_full=cinv_full, cgd_full=cgd_full, params=params, cbg=np.zeros((1, n - 1, d)))
+    engine.set_models(mb)
+    res = 8
+    s = new_scans(1)
+    s["v0"][0, :d] = -rng.uniform(1.2, 2.8, size=d)
+    s["dx"][0, 0], s["dy"][0, 1] = -0.6 / res, -0.6 / res
+    s["nx"], s["ny"], s["peak_width"] = res, res, 0.2
+    z, nn = engine.scan_open_host(s, n_type=N_F64, flags=0)
+    z_ref, n_ref, gap = oracle_batch(mb, s, 0)
+    # the construction really yields a single sector
+    from oracle import composer, path_b
+    from util import oracle_model
+    m = oracle_model(mb, 0, 0)
+    v = composer.affine_grid(s["v0"][0, :mb.n_volt], s["dx"][0, :mb.n_volt], s["dy"][0, :mb.n_volt], res, res).reshape(-1, mb.n_volt)
+    g = v @ np.asarray(m.cgd).T
+    st = path_b.select_charge_states(g, path_b.continuous_ground_state(g, m.cdd_inv), m.cdd_inv, 32, 1000)
+    widths = np.array([np.unique(t, return_counts=True)[1].max() for t in st.sum(axis=-1)])
+    assert (widths > 16).mean() > 0.5, widths
+    ok = gap.reshape(-1) > GAP_MIN
+    assert ok.mean() > 0.8
+    np.testing.assert_allclose(nn.reshape(-1, n)[ok], n_ref.reshape(-1, n)[ok], rtol=0, atol=N_ATOL)
+    np.testing.assert_allclose(z.reshape(-1)[ok], z_ref.reshape(-1)[ok], rtol=1e-5, atol=1e-7)
