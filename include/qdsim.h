@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 1
+#define QD_ABI_VERSION 2
 #define QD_MAX_DOTS 8   /* BASELINE.json configs go to 8 dots                                  */
 #define QD_MAX_VOLT 16  /* n_gate + n_barrier = (N+1) + (N-1)                                  */
 
@@ -63,6 +63,10 @@ typedef struct qd_env_params {
   double p_inter[QD_MAX_DOTS * QD_MAX_DOTS]; /* LatchingModel.p_inter, row-major, stride QD_MAX_DOTS        */
   double tc_base;                          /* BarrierVoltageModel.tc_base            (QD_ALG_TUNNEL)        */
   double alpha[QD_MAX_DOTS];               /* BarrierVoltageModel.alpha[n_barrier]   (QD_ALG_TUNNEL)        */
+  double vc_alpha, vc_beta;                /* create_linear_capacitance_model(alpha, beta) (QD_ALG_TUNNEL):  */
+                                           /* cdd *= 1 + vc_alpha mean|v|, cgd *= 1 + vc_beta mean|v| per    */
+                                           /* pixel in the ground state (voltage_dependent_capacitance.py:   */
+                                           /* 78-91, 128-141); 0, 0 = constant capacitances                  */
   int32_t max_charge_carriers;             /* brute_force                                                   */
   int32_t latching;                        /* 0: env has no LatchingModel                                   */
   int32_t reserved[2];

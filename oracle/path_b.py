@@ -13,6 +13,11 @@ literal, in NumPy fp64, following
 * src/qarray_latched/DotArrays/hamiltonian_build.py:12-45       (free energy of the kept states, recomputed unmasked)
 * src/qarray_latched/DotArrays/hamiltonian_build.py:75-137      (nearest-neighbour tunnelling, ``fermionic_negative``)
 * src/qarray_latched/DotArrays/hamiltonian_build.py:460-483     (diag(F))
+* src/qarray_latched/DotArrays/voltage_dependent_capacitance.py:78-91, 128-141 and ground_state.py:53-58 (optional
+                                                                  linear model: per pixel ``cdd = cdd_0 (1 + alpha mean|v|)``,
+                                                                  ``cgd = cgd_0 (1 + beta mean|v|)`` over ALL entries of v_ext;
+                                                                  in the ground state only -- the sensor keeps the constant
+                                                                  matrices, TunnelCoupledChargeSensed.py:342-376)
 * src/qarray_latched/DotArrays/barrier_voltage_model.py:55-151  (``vb_eff = vb + Cbg vg``; the cross-barrier term is the
                                                                   diagonal of a zero-diagonal matrix = 0;
                                                                   ``t = tc_base exp(-alpha vb_eff)``, no abs)
@@ -27,16 +32,18 @@ from __future__ import annotations
 import numpy as np
 
 
-def continuous_ground_state(g: np.ndarray, cinv: np.ndarray) -> np.ndarray:
-    """charge_states.py:36-88 -- ``g`` (P, N) = cgd[:N] @ v_ext."""
+def continuous_ground_state(g: np.ndarray, cinv: np.ndarray, scale=None) -> np.ndarray:
+    """charge_states.py:36-88 -- ``g`` (P, N) = cgd[:N] @ v_ext; ``scale`` (P,): per-pixel factor of cdd (cdd_inv is
+    divided by it), None = 1."""
     n_c = g.copy()
     bad = (g < 0).any(axis=1)
     if bad.any():
         gb = g[bad]
         n = np.clip(gb, 0, None)
-        cg = gb @ cinv.T                               # cdd_inv @ (cgd @ v)
+        sc = 1.0 if scale is None else np.asarray(scale)[bad][:, None]
+        cg = (gb @ cinv.T) / sc                        # cdd_inv @ (cgd @ v)
         for _ in range(50):
-            grad = n @ cinv.T - cg
+            grad = (n @ cinv.T) / sc - cg
             n = np.clip(n - 0.1 * grad, 0, None)
         n_c[bad] = n
     return np.clip(n_c, 0, None)
@@ -133,10 +140,18 @@ def ground_state_open(m, v_ext, return_gap: bool = False, chunk: int = 128):
     for s0 in range(0, v_ext.shape[0], chunk):
         v = v_ext[s0:s0 + chunk]
         g = v @ a.T
-        n_c = continuous_ground_state(g, cinv)
-        states = select_charge_states(g, n_c, cinv, m.num_charge_states, m.charge_state_batch_size)
+        s_c = None
+        if getattr(m, "vc_alpha", 0.0) or getattr(m, "vc_beta", 0.0):
+            vmean = np.abs(v).mean(axis=1)
+            s_c = 1.0 + m.vc_alpha * vmean
+            g = g * (1.0 + m.vc_beta * vmean)[:, None]
+        n_c = continuous_ground_state(g, cinv, s_c)
+        states = select_charge_states(g, n_c, cinv, m.num_charge_states, m.charge_state_batch_size)   # order is scale-free
         t = tunnel_couplings(m, v)
-        h, _ = hamiltonian(states, g, cinv, t)
+        h, f = hamiltonian(states, g, cinv, t)
+        if s_c is not None:                              # diag(F) / s_c: remove F, add it back scaled
+            idx = np.arange(h.shape[1])
+            h[:, idx, idx] += f / s_c[:, None] - f
         w, vec = np.linalg.eigh(h)
         psi2 = np.abs(vec[:, :, 0]) ** 2
         out[s0:s0 + chunk] = np.einsum("pm,pmd->pd", psi2, states.astype(np.float64))

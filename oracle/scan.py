@@ -40,6 +40,8 @@ class Model:
     alpha: np.ndarray | None = None
     num_charge_states: int = 32
     charge_state_batch_size: int = 1000
+    vc_alpha: float = 0.0          # create_linear_capacitance_model(alpha, beta); 0, 0 = constant capacitances
+    vc_beta: float = 0.0
 
 
 @dataclass

@@ -196,7 +196,7 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   a.rows_per_item = (int)rows;
   a.items_per_scan = (max_ny + a.rows_per_item - 1) / a.rows_per_item;
   const long long total_items = (long long)n_scan * a.items_per_scan;
-  const int wpc = (total_items < (long long)ctx->sm_count * 4) ? 1 : 4;
+  const int wpc = (total_items < (long long)ctx->sm_count * 4) ? 1 : QD_CTA_WARPS;
   long long grid = (total_items + wpc - 1) / wpc;
   if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
   const size_t smem = (size_t)a.slot_bytes * wpc;
@@ -383,6 +383,10 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
     if (alg == QD_ALG_BRUTE_FORCE && (p.max_charge_carriers < 0 || p.max_charge_carriers > 15))
       return fail(ctx, QD_ERR_INVALID, "env %d: max_charge_carriers must be in 0..15", e);
     if (!(p.kT >= 0.0)) return fail(ctx, QD_ERR_INVALID, "env %d: kT must be >= 0", e);
+    if ((p.vc_alpha != 0.0 || p.vc_beta != 0.0) && alg != QD_ALG_TUNNEL)
+      return fail(ctx, QD_ERR_UNSUPPORTED, "env %d: voltage-dependent capacitances exist on the tunnel path only", e);
+    if (!(p.vc_alpha >= 0.0) || !(p.vc_beta >= 0.0))
+      return fail(ctx, QD_ERR_INVALID, "env %d: vc_alpha / vc_beta must be >= 0", e);
     memcpy(r + L.o_cinv, cdd_inv_gs + (size_t)e * N * N, sizeof(double) * N * N);
     if (cdd_gs) memcpy(r + L.o_cdd, cdd_gs + (size_t)e * N * N, sizeof(double) * N * N);
     const double* cg = cgd_full + (size_t)e * D * NV;
@@ -403,6 +407,8 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
     par[QD_PAR_LATCH] = p.latching ? 1.0 : 0.0;
     par[QD_PAR_MAXC] = (double)p.max_charge_carriers;
     par[QD_PAR_TC_BASE] = p.tc_base;
+    par[QD_PAR_VC_ALPHA] = p.vc_alpha;
+    par[QD_PAR_VC_BETA] = p.vc_beta;
     for (int j = 0; j < 8; ++j) r[L.o_alpha + j] = p.alpha[j];
     for (int j = 0; j < 8; ++j) r[L.o_pleads + j] = p.p_leads[j];
     for (int j = 0; j < 64; ++j) r[L.o_pinter + j] = p.p_inter[j];

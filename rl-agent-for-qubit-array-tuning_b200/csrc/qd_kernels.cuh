@@ -64,6 +64,9 @@ __host__ __device__ inline int qd_slot_bytes(const qd_layout& L) {
 #ifndef QD_MIN_BLOCKS
 #define QD_MIN_BLOCKS 3
 #endif
+#ifndef QD_CTA_WARPS
+#define QD_CTA_WARPS 4          // warps per CTA of qd_scan_kernel (the warps are independent: any value works)
+#endif
 constexpr int QD_PC_WAYS = 8;
 
 // y = M x for a row-major N x N fp64 matrix in shared memory (16-byte aligned), all lanes reading the same elements:
@@ -462,7 +465,7 @@ __device__ __forceinline__ uint64_t pack_key(const double (&nd)[N]) {
 }
 
 template <int N, int ALG>
-__global__ void __launch_bounds__(128, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs a) {
+__global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs a) {
   extern __shared__ __align__(128) unsigned char qd_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;

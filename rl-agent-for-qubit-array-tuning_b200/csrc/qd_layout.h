@@ -17,6 +17,8 @@ enum {
   QD_PAR_LATCH = 7,       // 1.0 if the env has a LatchingModel
   QD_PAR_MAXC = 8,        // max_charge_carriers
   QD_PAR_TC_BASE = 9,
+  QD_PAR_VC_ALPHA = 10,   // linear voltage-dependent capacitance model (tunnel path), 0 = off
+  QD_PAR_VC_BETA = 11,
   QD_PAR_COUNT = 12
 };
 

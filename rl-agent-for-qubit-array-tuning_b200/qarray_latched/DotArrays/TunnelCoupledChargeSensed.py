@@ -100,9 +100,16 @@ class TunnelCoupledChargeSensed:
 
     # ---- device constants ----------------------------------------------------------------------------------
     def _model_batch(self) -> ModelBatch:
-        if self.voltage_capacitance_model is not None:
-            raise NotImplementedError("voltage-dependent capacitances are not wired into the kernel "
-                                      "(qarray_config.yaml:134 ships type: null)")
+        vcm = self.voltage_capacitance_model
+        if vcm is not None:
+            # the linear model of create_linear_capacitance_model as the facade builds it (qarray_base_class.py:846-851:
+            # cdd_0 = model.cdd_full, cgd_0 = model.cgd_full): two scalars per env, applied per pixel in the kernel
+            if getattr(vcm, "kind", None) != "linear":
+                raise NotImplementedError("only the linear voltage-dependent capacitance model is wired into the kernel")
+            if not (np.allclose(vcm.cdd_0, self.cdd_full, rtol=1e-12, atol=0) and
+                    np.allclose(vcm.cgd_0, self.cgd_full, rtol=1e-12, atol=0)):
+                raise NotImplementedError("the linear capacitance model must be built on the model's own cdd_full / "
+                                          "cgd_full (as qarray_base_class.py:846-851 does)")
         if not isinstance(self.num_charge_states, int):
             raise NotImplementedError("num_charge_states=None builds a dense 5^N x 5^N Hamiltonian per pixel in the "
                                       "reference (infeasible beyond N~3, SURVEY.md section 8a); pass an int (32)")
@@ -126,6 +133,8 @@ class TunnelCoupledChargeSensed:
             params["alpha"][0, :self.n_barrier] = np.asarray(self.barrier_model.alpha, dtype=np.float64)
         else:
             params["tc_base"] = self.tc                   # constant nearest-neighbour coupling (ground_state.py:92-101)
+        if vcm is not None:
+            params["vc_alpha"], params["vc_beta"] = vcm.alpha, vcm.beta
         cbg = None
         if use_barriers:
             cbg = np.zeros((1, self.n_barrier, self.n_gate)) if self.Cbg is None else self.Cbg[None]

@@ -1,7 +1,9 @@
 """Voltage-dependent capacitance holder (src/qarray_latched/DotArrays/voltage_dependent_capacitance.py:78-168).
-The shipped configuration sets ``voltage_capacitance_model.type: null`` (qarray_config.yaml:134), so the reference never
-builds one on the hot path; the linear model is accepted and stored, and the kernel rejects it loudly until its per-pixel
-scaling ``1 + alpha * mean(abs(v))`` is wired in."""
+The shipped configuration sets ``voltage_capacitance_model.type: null`` (qarray_config.yaml:134); with ``type: linear`` the
+facade builds ``create_linear_capacitance_model(cdd_0=model.cdd_full, cgd_0=model.cgd_full, alpha, beta)``
+(qarray_base_class.py:846-851).  The model is two scalars: per pixel ``cdd = cdd_0 (1 + alpha mean|v|)``,
+``cgd = cgd_0 (1 + beta mean|v|)`` in the ground state (ground_state.py:53-58); the tunnel kernel applies them
+(``qd_env_params.vc_alpha / vc_beta``)."""
 from __future__ import annotations
 
 from dataclasses import dataclass

@@ -35,10 +35,10 @@ PARAMS_DTYPE = np.dtype([
     ("kT", "f8"), ("threshold", "f8"), ("white_amp", "f8"),
     ("tele_p01", "f8"), ("tele_p10", "f8"), ("tele_amp", "f8"),
     ("p_leads", "f8", (QD_MAX_DOTS,)), ("p_inter", "f8", (QD_MAX_DOTS * QD_MAX_DOTS,)),
-    ("tc_base", "f8"), ("alpha", "f8", (QD_MAX_DOTS,)),
+    ("tc_base", "f8"), ("alpha", "f8", (QD_MAX_DOTS,)), ("vc_alpha", "f8"), ("vc_beta", "f8"),
     ("max_charge_carriers", "i4"), ("latching", "i4"), ("reserved", "i4", (2,)),
 ], align=True)
-assert PARAMS_DTYPE.itemsize == 712, PARAMS_DTYPE.itemsize
+assert PARAMS_DTYPE.itemsize == 728, PARAMS_DTYPE.itemsize
 
 
 class ModelDesc(C.Structure):
@@ -103,7 +103,7 @@ def load() -> C.CDLL:
     lib.qd_measure_fp64_peak.restype = C.c_int
     lib.qd_measure_fp32_peak.argtypes = [vp, C.c_int, dp]
     lib.qd_measure_fp32_peak.restype = C.c_int
-    if lib.qd_abi_version() != 1:
-        raise OSError(f"{path}: ABI version {lib.qd_abi_version()} != 1")
+    if lib.qd_abi_version() != 2:
+        raise OSError(f"{path}: ABI version {lib.qd_abi_version()} != 2")
     _lib = lib
     return lib

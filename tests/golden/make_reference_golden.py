@@ -34,10 +34,13 @@ CASES = {
     "ref_6dot_tunnel_identity_vgm": dict(n_dot=6, res=16, seed=14, pair=4, vgm="identity", cbb=True),
     "ref_8dot_tunnel_identity_vgm": dict(n_dot=8, res=12, seed=15, pair=5, vgm="identity", cbb=False),
     "ref_4dot_constant_tc_no_barriers": dict(n_dot=4, res=16, seed=16, pair=1, vgm="identity", cbb=False, barriers=False),
+    # voltage_capacitance_model.type: linear (qarray_config.yaml:103-105, 132-134; qarray_base_class.py:842-852)
+    "ref_4dot_tunnel_linear_capacitance": dict(n_dot=4, res=20, seed=17, pair=2, vgm="identity", cbb=False, vc=(0.08, 0.06)),
+    "ref_6dot_tunnel_linear_capacitance": dict(n_dot=6, res=12, seed=18, pair=3, vgm="perfect", cbb=False, vc=(0.05, 0.10)),
 }
 
 
-def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True):
+def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True, vc=None):
     """Raw inputs of one case, drawn with the reference's sampling ranges (qdsim.synth)."""
     from qdsim import synth
     dev = synth.sample_barrier_devices(1, n_dot, seed=seed)
@@ -53,7 +56,7 @@ def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True):
     raw["barrier_voltages"] = rng.uniform(-1.0, 3.0, size=B)
     raw["half"] = float(rng.uniform(1.5, 2.0))
     raw["centre_offset"] = rng.uniform(-2.0, 2.0, size=n_dot) + offset
-    raw.update(res=res, pair=pair, vgm_kind=vgm)
+    raw.update(res=res, pair=pair, vgm_kind=vgm, vc=np.array(vc if vc is not None else (0.0, 0.0)))
     return raw
 
 
@@ -72,6 +75,12 @@ def run_reference(raw):
             T=raw["T"], max_charge_carriers=4, tc=raw["tc"], noise_model=None, latching_model=None,
             voltage_capacitance_model=None, use_sparse=False, num_charge_states=32, charge_state_batch_size=1000,
             charge_carrier="electrons", **kw)
+        if raw["vc"].any():                              # qarray_base_class.py:846-852
+            vdc = sys.modules["qarray_latched.DotArrays.voltage_dependent_capacitance"]
+            import jax.numpy as jnp
+            model.voltage_capacitance_model = vdc.create_linear_capacitance_model(
+                cdd_0=jnp.array(model.cdd_full), cgd_0=jnp.array(model.cgd_full), alpha=float(raw["vc"][0]),
+                beta=float(raw["vc"][1]))
         comp = model.gate_voltage_composer
         perfect_vgm = np.array(comp.virtual_gate_matrix)
         if raw["vgm_kind"] == "identity":                # qarray_base_class.py:868-877 (electrons: -I)

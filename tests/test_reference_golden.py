@@ -25,7 +25,8 @@ from oracle import scan as oscan
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CASES = ["ref_4dot_tunnel_identity_vgm", "ref_4dot_tunnel_perfect_vgm_cbb", "ref_5dot_tunnel_low_occupancy",
-             "ref_6dot_tunnel_identity_vgm", "ref_8dot_tunnel_identity_vgm", "ref_4dot_constant_tc_no_barriers"]
+             "ref_6dot_tunnel_identity_vgm", "ref_8dot_tunnel_identity_vgm", "ref_4dot_constant_tc_no_barriers",
+             "ref_4dot_tunnel_linear_capacitance", "ref_6dot_tunnel_linear_capacitance"]
 GAP_TOL = 1e-6            # spectral gap below which <n> is not unique
 N_ATOL_CPU = 1e-11        # LAPACK (reference run) vs LAPACK (oracle); measured 5e-14
 N_ATOL_GPU = 2e-6         # Householder + Sturm multisection + inverse iteration on the GPU (tests/test_tunnel_gpu.py)
@@ -45,8 +46,11 @@ def product_model(d):
     from qdsim import maxwell
     n = d["Cdd"].shape[0]
     if d["barriers"]:
-        return tunnel_model_batch(d["Cdd"][None], d["Cgd"][None], d["Cds"][None], d["Cgs"][None], d["Cbd"][None],
-                                  d["Cbg"][None], d["Cbs"][None], float(d["tc_base"]), d["alpha"][None])
+        mb = tunnel_model_batch(d["Cdd"][None], d["Cgd"][None], d["Cds"][None], d["Cgs"][None], d["Cbd"][None],
+                                d["Cbg"][None], d["Cbs"][None], float(d["tc_base"]), d["alpha"][None])
+        if "vc" in d:
+            mb.params["vc_alpha"], mb.params["vc_beta"] = d["vc"]
+        return mb
     cdd_nm, cgd_nm = maxwell.embed_sensor(d["Cdd"][None], d["Cgd"][None], d["Cds"][None], d["Cgs"][None])
     _, cdd_inv_full, cgd_full = maxwell.maxwell(cdd_nm, cgd_nm)
     params = np.zeros(1, dtype=PARAMS_DTYPE)
@@ -130,11 +134,16 @@ def _drop_in(d, device=0):
         kw = dict(Cbd=d["Cbd"], Cbg=d["Cbg"], Cbs=d["Cbs"], Cbb=d.get("Cbb"),
                   barrier_model=BarrierVoltageModel(n_barrier=n - 1, n_dot=n, tc_base=float(d["tc_base"]),
                                                     alpha=list(d["alpha"])))
-    return TunnelCoupledChargeSensed(
+    model = TunnelCoupledChargeSensed(
         Cdd=d["Cdd"], Cgd=d["Cgd"], Cds=d["Cds"], Cgs=d["Cgs"], coulomb_peak_width=float(d["peak_width"]),
         T=float(d["T"]), max_charge_carriers=4, tc=float(d["tc"]), noise_model=None, latching_model=None,
         voltage_capacitance_model=None, use_sparse=False, num_charge_states=32, charge_state_batch_size=1000,
         charge_carrier="electrons", device=device, **kw)
+    if "vc" in d and d["vc"].any():                      # qarray_base_class.py:846-852
+        from qarray_latched.DotArrays.voltage_dependent_capacitance import create_linear_capacitance_model
+        model.voltage_capacitance_model = create_linear_capacitance_model(
+            cdd_0=model.cdd_full, cgd_0=model.cgd_full, alpha=float(d["vc"][0]), beta=float(d["vc"][1]))
+    return model
 
 
 @pytest.mark.gpu

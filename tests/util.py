@@ -23,7 +23,7 @@ def oracle_model(mb, e: int, flags: int = 0):
         tele_p10=float(p["tele_p10"]), tele_amp=float(p["tele_amp"]) if noise else 0.0,
         n_gate=mb.n_gate, cbg=None if mb.cbg is None else mb.cbg[e], tc_base=float(p["tc_base"]),
         alpha=p["alpha"].copy(), num_charge_states=mb.num_charge_states,
-        charge_state_batch_size=mb.charge_state_batch_size)
+        charge_state_batch_size=mb.charge_state_batch_size, vc_alpha=float(p["vc_alpha"]), vc_beta=float(p["vc_beta"]))
 
 
 def oracle_scan(rec, n_volt: int, flags: int = 0):
@@ -68,6 +68,22 @@ def compare_charges(n_gpu, n_ref, margin, tie_tol=1e-9, max_tie_frac=0.005):
     return int((~safe).sum())
 
 
+def _params_from_bytes(raw):
+    """Fixture bytes -> current PARAMS_DTYPE (fixtures made before ABI 2 lack the vc_alpha / vc_beta fields)."""
+    from qdsim import PARAMS_DTYPE
+    raw = np.ascontiguousarray(raw)
+    if raw.size % PARAMS_DTYPE.itemsize == 0:
+        return raw.view(PARAMS_DTYPE).copy()
+    legacy = np.dtype([(n, PARAMS_DTYPE.fields[n][0]) for n in PARAMS_DTYPE.names if n not in ("vc_alpha", "vc_beta")],
+                      align=True)
+    assert legacy.itemsize == 712 and raw.size % 712 == 0, (legacy.itemsize, raw.size)
+    old = raw.view(legacy)
+    out = np.zeros(old.shape, dtype=PARAMS_DTYPE)
+    for n in legacy.names:
+        out[n] = old[n]
+    return out
+
+
 def load_golden(name):
     """tests/golden/<name>.npz -> (ModelBatch, scans, flags, z, n, margin): inputs rebuilt through the product's host code
     from the RAW capacitances stored in the fixture."""
@@ -76,7 +92,7 @@ def load_golden(name):
     from qdsim.engine import ModelBatch
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz")
     d = np.load(path)
-    params = d["params"].view(PARAMS_DTYPE).copy()
+    params = _params_from_bytes(d["params"])
     if str(d["algorithm"]) == "tunnel":
         from qdsim.engine import tunnel_model_batch
         mb = tunnel_model_batch(d["Cdd"], d["Cgd"], d["Cds"], d["Cgs"], d["Cbd"], d["Cbg"], d["Cbs"],
