@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
     const double* par = rec + L.o_par;
     const bool replace = (a.flags & QD_FLAG_RADIAL) && sc->rad_mode == 2;
     const long long pix0 = sc->pix_offset;
+    const bool vc_on = par[QD_PAR_VC_ALPHA] != 0.0 || par[QD_PAR_VC_BETA] != 0.0;
 
     // ---- per-item split of the dots into a high and a low half ----
     // Any split is exact; its only job is to make the block bound bite.  Dots that are empty and far below their
@@ -290,17 +291,19 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
           __syncwarp();
           {
             if (lane < N) {
-              double acc = 0.0, vabs = 0.0;
+              double acc = 0.0;
               const double* arow = rec + L.o_a + lane * NV;
-              for (int k = 0; k < NV; ++k) {
-                acc = fma(arow[k], vv[k], acc);
-                vabs += fabs(vv[k]);
+              for (int k = 0; k < NV; ++k) acc = fma(arow[k], vv[k], acc);
+              if (vc_on) {
+                // linear voltage-dependent capacitances (voltage_dependent_capacitance.py:78-91): cgd scales by
+                // 1 + beta mean|v|, cdd by 1 + alpha mean|v| (so cdd^-1 by its inverse)
+                double vabs = 0.0;
+                for (int k = 0; k < NV; ++k) vabs += fabs(vv[k]);
+                const double vmean = vabs / (double)NV;
+                acc *= fma(par[QD_PAR_VC_BETA], vmean, 1.0);
+                if (lane == 0) ts[7] = fma(par[QD_PAR_VC_ALPHA], vmean, 1.0);
               }
-              // linear voltage-dependent capacitances (voltage_dependent_capacitance.py:78-91): cgd scales by
-              // 1 + beta mean|v|, cdd by 1 + alpha mean|v| (so cdd^-1 by its inverse); both factors are exactly 1 when off
-              const double vmean = vabs / (double)NV;
-              gs[lane] = acc * fma(par[QD_PAR_VC_BETA], vmean, 1.0);
-              if (lane == 0) ts[7] = fma(par[QD_PAR_VC_ALPHA], vmean, 1.0);
+              gs[lane] = acc;
             }
             if (lane >= 16 && lane < 16 + B) {
               const int d = lane - 16;
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               cg += shfl_f64(cg, lane ^ 1);
               cg += shfl_f64(cg, lane ^ 2);
               ni = fmax(gi, 0.0);
-              const double lr = 0.1 / ts[7];           // the gradient carries cdd^-1 / s_c
+              const double lr = vc_on ? 0.1 / ts[7] : 0.1;       // the gradient carries cdd^-1 / s_c
               for (int it = 0; it < 50; ++it) {
                 double part = fma(c0, shfl_f64(ni, l0), c1 * shfl_f64(ni, l1));
                 part += shfl_f64(part, lane ^ 1);
@@ -526,7 +529,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               for (int j = 0; j < N; ++j) s = fma(C[i * N + j], zz[j], s);
               Fm = fma(zz[i], s, Fm);
             }
-            Fm /= ts[7];
+            if (vc_on) Fm /= ts[7];
           }
           // Hopping conserves the total charge, so H is block diagonal once the basis is ordered by total charge: the
           // 32 kept states typically fall into 5-6 sectors of <= 10-16 states.  Sort the lanes by (total charge, lane)
