@@ -163,6 +163,14 @@ def cpu_reference_pixels_per_s(mb, scans, flags, n_sample_scans: int, cores: int
     return pixels / dt, pixels, dt, "port: NumPy restatement, one process per core"
 
 
+def cpu_reference_scan_seconds(mb, scans, flags, threads: int) -> float:
+    """Wall time of ONE pass of the C restatement over ``scans`` on ``threads`` threads (latency of small cases; the
+    first call spins the thread pool up and is discarded)."""
+    from oracle import cport
+    cport.run_scans(mb, scans, flags, threads=threads)
+    return cport.run_scans(mb, scans, flags, threads=threads)[2]
+
+
 def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int, path: str = "A"):
     from qdsim import synth
     if path == "B":

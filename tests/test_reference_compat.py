@@ -86,3 +86,19 @@ def test_reference_facade_builds_the_barrier_model_through_our_classes(reference
     # the composer call the facade makes every step (qarray_base_class.py:143-154)
     vg = m.gate_voltage_composer.do2d("vP1", -1.0, 1.0, 32, "vP2", -1.0, 1.0, 32, np.zeros(5), True)
     assert vg.shape == (32, 32, 5)
+
+
+def test_reference_facade_with_linear_voltage_capacitance(reference_facade, tmp_path):
+    """``voltage_capacitance_model.type: linear`` (qarray_config.yaml:132-134): the facade builds the linear model on the
+    model's own matrices (qarray_base_class.py:842-852) and our class turns it into the two kernel parameters."""
+    import yaml
+    cfg_path = os.path.join(REF, "qadapt", "environment", "qarray_config.yaml")
+    cfg = yaml.safe_load(open(cfg_path))
+    cfg["simulator"]["voltage_capacitance_model"]["type"] = "linear"
+    p = tmp_path / "qarray_config_linear.yaml"
+    p.write_text(yaml.safe_dump(cfg))
+    base = reference_facade.QarrayBaseClass(num_dots=4, use_barriers=True, obs_image_size=16, config_path=str(p))
+    m = base.model
+    assert m.voltage_capacitance_model is not None and m.voltage_capacitance_model.kind == "linear"
+    mb = m._model_batch()
+    assert 0.05 <= mb.params["vc_alpha"][0] <= 0.10 and 0.05 <= mb.params["vc_beta"][0] <= 0.10

@@ -47,14 +47,11 @@ def time_gpu(eng, mb, scans, n_type, steps=3, warmup=3):
 
 
 def time_cpu(mb, scans, budget_s=3.0):
-    from oracle import cport
+    """CPU comparator = bench.py's cpu_baseline leg (the only place besides tests/ that may execute oracle/)."""
+    import bench
     cores = os.cpu_count() or 1
-    cal = min(len(scans), 2 * cores)
-    cport.time_scans(mb, scans[:cal], FLAGS, threads=cores)
-    rate, pix, dt = cport.time_scans(mb, scans[:cal], FLAGS, threads=cores)
-    n = int(min(len(scans), max(cal, budget_s * rate / (pix / cal))))
-    pps, pixels, dt = cport.time_scans(mb, scans[:n], FLAGS, threads=cores)
-    return {"pixels_per_s": pps, "cores": cores, "sample_scans": n, "seconds": dt}
+    pps, pixels, dt, _ = bench.cpu_reference_pixels_per_s(mb, scans, FLAGS, 0, cores, budget_s=budget_s)
+    return {"pixels_per_s": pps, "cores": cores, "sample_scans": pixels // int(scans["nx"][0] * scans["ny"][0]), "seconds": dt}
 
 
 def next_rows(eng, out, quick=False):
@@ -124,15 +121,14 @@ def main():
     for _ in range(200):
         m.do2d_open(1, -3.3, 0.7, 64, 2, -3.1, 0.9, 64)
     lat = (time.perf_counter() - t0) / 200
-    from oracle import cport
+    import bench
     from qdsim.engine import new_scans
     mb1 = m._model_batch()
     s1 = new_scans(1)
     v0, dx, dy = m.gate_voltage_composer.affine2d(1, -3.3, 0.7, 64, 2, -3.1, 0.9, 64)
     s1["v0"][0, :3], s1["dx"][0, :3], s1["dy"][0, :3], s1["nx"], s1["ny"], s1["peak_width"] = v0, dx, dy, 64, 64, 0.15
-    cport.run_scans(mb1, s1, 0, threads=os.cpu_count())
-    _, _, dt_cpu = cport.run_scans(mb1, s1, 0, threads=os.cpu_count())
-    _, _, dt_cpu1 = cport.run_scans(mb1, s1, 0, threads=1)
+    dt_cpu = bench.cpu_reference_scan_seconds(mb1, s1, 0, os.cpu_count())
+    dt_cpu1 = bench.cpu_reference_scan_seconds(mb1, s1, 0, 1)
     out["config1_2dot_64x64_single_do2d_open"] = {
         "gpu_call_latency_us": lat * 1e6, "note": "Python do2d_open -> qd_scan_open_host, host buffers, synchronous",
         "cpu_cport_all_cores_us": dt_cpu * 1e6, "cpu_cport_1_core_us": dt_cpu1 * 1e6}
