@@ -295,6 +295,10 @@ def main():
     from qdsim import Engine
 
     torch.cuda.set_device(local_rank)
+    numa_bound = False
+    if world > 1 and os.environ.get("QDSIM_NO_NUMA_BIND") != "1":
+        from qdsim import parallel as _par
+        numa_bound = _par.bind_to_gpu_numa_node(local_rank)      # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
@@ -438,6 +442,7 @@ def main():
         assert full.shape == (args.n_env * world, 2)
         if rank == 0:
             out["episode_stats_allgather"] = {"shape": list(full.shape), "ranks_seen": int(full[:, 1].unique().numel())}
+            out["numa_bound"] = bool(numa_bound)
     barrier()
     if world > 1:
         dist.destroy_process_group()

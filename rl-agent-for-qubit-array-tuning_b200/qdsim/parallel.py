@@ -8,8 +8,49 @@ once per rollout, in env order, over NCCL (gloo in the CPU tests).
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
+
+
+def gpu_numa_cpus(device: int):
+    """CPUs of the NUMA node the GPU hangs off, or None if the platform does not say.  PCI address from the CUDA device
+    properties (so CUDA_VISIBLE_DEVICES remaps are honoured), NUMA node and CPU list from sysfs."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        return cpus or None
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
+def bind_to_gpu_numa_node(device: int) -> bool:
+    """Pin this process to the CPUs next to its GPU BEFORE it allocates pinned host buffers, so that those buffers (first
+    touch) and the copy engine's traffic stay on the GPU's own socket.  With one process per GPU on a two-socket box,
+    unbound ranks all land their staging buffers wherever the scheduler started them and the device-to-host image copies
+    of half the GPUs cross the socket interconnect.  Returns False (and changes nothing) when the topology is unknown."""
+    cpus = gpu_numa_cpus(device)
+    if not cpus:
+        return False
+    try:
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return False
+        os.sched_setaffinity(0, allowed)
+        return True
+    except (OSError, AttributeError):
+        return False
 
 
 def shard_range(n_env: int, rank: int, world: int) -> tuple[int, int]:

@@ -59,3 +59,14 @@ def test_shard_ranges_partition_the_envs():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         parallel.shard_range(4, 4, 4)
+
+
+def test_numa_binding_is_a_no_op_without_topology():
+    """No GPU / no sysfs entry: the helper reports False and leaves the affinity alone."""
+    import os
+    from qdsim import parallel
+    before = os.sched_getaffinity(0)
+    assert parallel.gpu_numa_cpus(0) is None or isinstance(parallel.gpu_numa_cpus(0), set)
+    ok = parallel.bind_to_gpu_numa_node(0)
+    assert ok or os.sched_getaffinity(0) == before
+    os.sched_setaffinity(0, before)
