@@ -6,6 +6,9 @@
 #include <string.h>
 
 #include <new>
+#include <stdlib.h>
+
+#include <algorithm>
 #include <vector>
 
 #include "qd_kernels.cuh"
@@ -140,7 +143,7 @@ int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) 
 
 // enqueue one launch over device-resident descriptors
 int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const double* d_points, float* d_z, void* d_n,
-           int n_type, unsigned flags, cudaStream_t stream) {
+           int n_type, unsigned flags, cudaStream_t stream, int rows_cap = 0) {
   kernel_fn fn = pick_kernel(ctx->L);
   if (!fn) return fail(ctx, QD_ERR_UNSUPPORTED, "no kernel for n_dot=%d algorithm=%d", ctx->L.n_dot, ctx->L.algorithm);
   qd::KArgs a;
@@ -192,6 +195,8 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   long long rows = ((long long)n_scan * max_ny) / target_items;
   if (rows < 1) rows = 1;
   if (rows > max_ny) rows = max_ny;
+  // a pipelined caller launches several times per batch: shorter items keep the idle tail of each launch short
+  if (rows_cap > 0 && rows > rows_cap) rows = rows_cap;
   if (flags & QD_FLAG_CARRY_ROWS) rows = max_ny;
   a.rows_per_item = (int)rows;
   a.items_per_scan = (max_ny + a.rows_per_item - 1) / a.rows_per_item;
@@ -214,24 +219,6 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
 int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stream, int* max_ny) {
   if (n_scan <= 0) return fail(ctx, QD_ERR_INVALID, "n_scan must be positive");
   if (!scans) return fail(ctx, QD_ERR_INVALID, "scans is NULL");
-  int mny = 0;
-  long long ext = 0, mpix = 0;
-  for (int i = 0; i < n_scan; ++i) {
-    const qd_scan& s = scans[i];
-    const long long np_ = (long long)s.nx * s.ny;
-    if (s.pix_offset + np_ > ext) ext = s.pix_offset + np_;
-    if (np_ > mpix) mpix = np_;
-    if (s.env_id < 0 || s.env_id >= ctx->n_env)
-      return fail(ctx, QD_ERR_INVALID, "scan %d: env_id %d out of range [0,%d)", i, s.env_id, ctx->n_env);
-    if (s.nx <= 0 || s.ny <= 0) return fail(ctx, QD_ERR_INVALID, "scan %d: nx, ny must be positive", i);
-    if (s.pix_offset < 0) return fail(ctx, QD_ERR_INVALID, "scan %d: negative pix_offset", i);
-    if (s.ny > mny) mny = s.ny;
-  }
-  *max_ny = mny;
-  ctx->up_n_scan = n_scan;
-  ctx->up_max_ny = mny;
-  ctx->up_pixels = ext;
-  ctx->up_max_pix = mpix;
   const size_t bytes = (size_t)n_scan * sizeof(qd_scan);
   int rc = grow(ctx, &ctx->d_scans, &ctx->scans_cap, bytes);
   if (rc) return rc;
@@ -254,8 +241,28 @@ int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stre
     memcpy(ctx->h_scans, scans, bytes);
     src = ctx->h_scans;
   }
+  // the copy is issued first and runs while the host validates the descriptors (nothing is launched on a failure)
   QD_CUDA(ctx, cudaMemcpyAsync(ctx->d_scans, src, bytes, cudaMemcpyHostToDevice, stream));
   QD_CUDA(ctx, cudaEventRecord(ctx->staged, stream));
+  ctx->up_n_scan = 0;
+  int mny = 0;
+  long long ext = 0, mpix = 0;
+  for (int i = 0; i < n_scan; ++i) {
+    const qd_scan& s = scans[i];
+    const long long np_ = (long long)s.nx * s.ny;
+    if (s.pix_offset + np_ > ext) ext = s.pix_offset + np_;
+    if (np_ > mpix) mpix = np_;
+    if (s.env_id < 0 || s.env_id >= ctx->n_env)
+      return fail(ctx, QD_ERR_INVALID, "scan %d: env_id %d out of range [0,%d)", i, s.env_id, ctx->n_env);
+    if (s.nx <= 0 || s.ny <= 0) return fail(ctx, QD_ERR_INVALID, "scan %d: nx, ny must be positive", i);
+    if (s.pix_offset < 0) return fail(ctx, QD_ERR_INVALID, "scan %d: negative pix_offset", i);
+    if (s.ny > mny) mny = s.ny;
+  }
+  *max_ny = mny;
+  ctx->up_n_scan = n_scan;
+  ctx->up_max_ny = mny;
+  ctx->up_pixels = ext;
+  ctx->up_max_pix = mpix;
   return QD_OK;
 }
 
@@ -494,11 +501,28 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   // Large batches run as a pipeline: the scans are cut into chunks whose output pixel ranges are disjoint and
   // increasing; chunk c+1 computes on one stream while chunk c's images travel back over PCIe on another.
   int n_chunk = n_scan / 2048;          // >= 2048 scans per chunk keeps every launch a full-chip wave or more
-  if (n_chunk > 8) n_chunk = 8;        // measured: 16 chunks are no faster (more partial waves at the launch tails)
+  int chunk_cap = 8, rows_cap = 16;    // measured (tools/flagtime.py, profiles/): see DESIGN.md "host-buffer pipeline"
+  if (const char* e = getenv("QDSIM_PIPE_CHUNKS")) chunk_cap = atoi(e) > 0 ? atoi(e) : chunk_cap;
+  if (const char* e = getenv("QDSIM_PIPE_ROWS")) rows_cap = atoi(e) > 0 ? atoi(e) : rows_cap;
+  if (chunk_cap > 16) chunk_cap = 16;   // chunk_done[16]
+  if (n_chunk > chunk_cap) n_chunk = chunk_cap;
   if (n_chunk < 1) n_chunk = 1;
   std::vector<int> cut(n_chunk + 1);
   std::vector<long long> lo(n_chunk), hi(n_chunk);
-  for (int c = 0; c <= n_chunk; ++c) cut[c] = (int)((long long)n_scan * c / n_chunk);
+  // Chunk sizes: equal, except that the last three halve (1, ..., 1, 1/2, 1/4, 1/8).  The copy of the LAST chunk is the
+  // only one that cannot hide behind compute, so it is kept small (about 2 % of the images at 8 chunks) as long as it
+  // still fills the chip.
+  {
+    std::vector<double> w(n_chunk, 1.0);
+    if (n_chunk >= 6) { w[n_chunk - 3] = 0.5; w[n_chunk - 2] = 0.25; w[n_chunk - 1] = 0.125; }
+    double tot = 0.0;
+    for (double x : w) tot += x;
+    if (n_chunk >= 6 && (double)n_scan * w[n_chunk - 1] / tot < 2048.0) { std::fill(w.begin(), w.end(), 1.0); tot = n_chunk; }
+    double acc = 0.0;
+    cut[0] = 0;
+    for (int c = 0; c < n_chunk; ++c) { acc += w[c]; cut[c + 1] = (int)((double)n_scan * acc / tot); }
+    cut[n_chunk] = n_scan;
+  }
   for (int c = 0; c < n_chunk; ++c) {
     long long a = -1, b = 0;
     for (int i = cut[c]; i < cut[c + 1]; ++i) {
@@ -514,7 +538,7 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   for (int c = 0; c < n_chunk; ++c) {
     ctx->up_pixels = all_pixels;      // the tunnel scratch is addressed with the scans' own pixel offsets
     rc = launch(ctx, cut[c + 1] - cut[c], ctx->d_scans + cut[c], max_ny, nullptr, ctx->d_z, ctx->d_n, n_type, flags,
-                ctx->s_compute);
+                ctx->s_compute, n_chunk > 1 ? rows_cap : 0);
     if (rc) return rc;
     QD_CUDA(ctx, cudaEventRecord(ctx->chunk_done[c], ctx->s_compute));
     QD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->chunk_done[c], 0));
