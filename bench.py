@@ -211,6 +211,15 @@ def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_e
            "kernels": f"qd_tunnel_gs_kernel<{n_dot}> + qd_scan_kernel<{n_dot},tunnel>",
            "value": pixels / (ms * 1e-3), "unit": "pixels/s", "env_steps_per_s": n_env / (ms * 1e-3),
            "ms_per_step": ms, "steps": steps, "cpu_baseline": None}
+    # no flop model for this path (data-dependent control flow); what bounds it is instruction issue: warp instructions
+    # per pixel from the committed ncu capture (profiles/r01_ncu_summary.md) against 4 issue slots per SM per clock
+    instr = {8: 13280.0, 4: 9500.0}.get(n_dot)
+    if instr:
+        props = torch.cuda.get_device_properties(0)
+        peak = props.multi_processor_count * 4 * 1.965e9
+        blk["issue_roofline"] = {"warp_instr_per_pixel": instr, "source": "ncu smsp__inst_executed.sum / pixels (profiles/)",
+                                 "achieved": blk["value"] * instr, "peak": peak, "unit": "warp-instr/s",
+                                 "frac": blk["value"] * instr / peak}
     if with_cpu:
         from util import oracle_batch
         small = scans[:1].copy()
