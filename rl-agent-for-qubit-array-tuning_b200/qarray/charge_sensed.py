@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_THERMAL, N_F64, N_NONE, maxwell
+from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_THERMAL, N_F64, maxwell
 from qdsim.composer import GateVoltageComposer
 from qdsim.engine import ModelBatch, new_scans
 from qdsim.runtime import engine_for, fresh_seed

@@ -56,7 +56,7 @@ def test_results_do_not_depend_on_batch_composition_or_launch_geometry(engine, f
 def test_certain_latching_is_the_identity_at_full_size(engine, full_batch):
     """p_leads = p_inter = 1 accepts every transition: the latched charge maps equal the unlatched ones everywhere."""
     import torch
-    from qdsim import FLAG_LATCH, N_NONE, N_U8
+    from qdsim import FLAG_LATCH, N_U8
     dev, mb, scans, z, n, flags = full_batch
     mb.params["p_leads"][:] = 1.0
     mb.params["p_inter"][:] = 1.0

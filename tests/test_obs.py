@@ -76,7 +76,7 @@ def test_percentile_normalisation_is_bit_exact_vs_numpy(engine, per_env, n_env):
 def test_observe_batch_end_to_end(engine):
     """obs_scans -> scan kernel -> normalisation, against the oracle + np.percentile env by env."""
     import torch
-    from qdsim import FLAG_LATCH, N_NONE, obs
+    from qdsim import FLAG_LATCH, obs
     from util import oracle_batch
     dev, mb, gv, vgm, origin, sv = _state(3, 4, 3)
     engine.set_models(mb)

@@ -1,7 +1,7 @@
 import sys, os
 sys.path.insert(0, os.path.join(os.getcwd(), "rl-agent-for-qubit-array-tuning_b200"))
-import numpy as np, torch
-from qdsim import Engine, synth, FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_U8, N_NONE
+import torch
+from qdsim import Engine, synth, FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_U8
 eng = Engine(0)
 dev = synth.sample_devices(4096, 8, seed=1234); mb = synth.model_batch(dev); eng.set_models(mb)
 sc = synth.env_step_scans(mb, dev, res=64, seed=99)
