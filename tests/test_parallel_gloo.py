@@ -36,6 +36,39 @@ def _worker(rank, world, port, n_env, out):
     dist.destroy_process_group()
 
 
+def _rollout_worker(rank, world, port, n_env, out):
+    """Each rank steps its own shard of envs (host logic only, no GPU) and the episode statistics meet on every rank."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "rl-agent-for-qubit-array-tuning_b200"))
+    import numpy as np
+    from qdsim import parallel
+    from qdsim.multi_agent import BatchedMultiAgentEnv
+    from qdsim.vector_env import BatchedDeviceEnv, EnvConfig
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lo, hi = parallel.shard_range(n_env, rank, world)
+    env = BatchedMultiAgentEnv(BatchedDeviceEnv(hi - lo, 3, engine=None, config=EnvConfig(resolution=8, max_steps=2),
+                                                seed=50 + rank))
+    env.reset()
+    rng = np.random.default_rng(rank)
+    for _ in range(2):
+        _, _, _, trunc, _ = env.step({a: rng.uniform(-1, 1, size=(hi - lo, 1)) for a in env.all_agent_ids}, skip_obs=True)
+    local = torch.from_numpy(env.episode_stats())
+    full = parallel.gather_episode_stats(local, n_env)
+    ok = trunc["__all__"] and full.shape == (n_env, 4) and torch.equal(full[lo:hi], local) and bool((full[:, 1] == 2).all())
+    out[rank] = bool(ok)
+    dist.destroy_process_group()
+
+
+def test_sharded_rollout_statistics_over_gloo():
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_rollout_worker, args=(2, port, 7, out), nprocs=2, join=True)
+        assert all(out[r] for r in range(2)) and len(out) == 2
+
+
 @pytest.mark.parametrize("world,n_env", [(2, 10), (3, 10), (2, 7)])
 def test_sharding_and_stat_gather_over_gloo(world, n_env):
     port = _free_port()
