@@ -37,10 +37,16 @@ CASES = {
     # voltage_capacitance_model.type: linear (qarray_config.yaml:103-105, 132-134; qarray_base_class.py:842-852)
     "ref_4dot_tunnel_linear_capacitance": dict(n_dot=4, res=20, seed=17, pair=2, vgm="identity", cbb=False, vc=(0.08, 0.06)),
     "ref_6dot_tunnel_linear_capacitance": dict(n_dot=6, res=12, seed=18, pair=3, vgm="perfect", cbb=False, vc=(0.05, 0.10)),
+    # the env's own regime (env.py:808-858): barriers up to +-15 V from their optimum, i.e. tunnel couplings from 1e-9 to 1e7,
+    # and windows tens of volts from the ground truth (occupations of 10-40 carriers on some dots, none on others)
+    "ref_4dot_tunnel_strong_coupling": dict(n_dot=4, res=16, seed=19, pair=2, vgm="identity", cbb=False, vb_shift=-8.0),
+    "ref_4dot_tunnel_closed_barriers": dict(n_dot=4, res=16, seed=20, pair=1, vgm="identity", cbb=False, vb_shift=+14.0),
+    "ref_6dot_tunnel_far_window": dict(n_dot=6, res=10, seed=21, pair=3, vgm="identity", cbb=False, offset=22.0, spread=12.0,
+                                       vb_shift=14.0),
 }
 
 
-def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True, vc=None):
+def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True, vc=None, vb_shift=0.0, spread=2.0):
     """Raw inputs of one case, drawn with the reference's sampling ranges (qdsim.synth)."""
     from qdsim import synth
     dev = synth.sample_barrier_devices(1, n_dot, seed=seed)
@@ -53,9 +59,9 @@ def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True, vc=
         raw["Cbb"] = c + c.T
     raw.update(tc_base=float(dev["tc_base"][0]), alpha=dev["alpha"][0], peak_width=float(dev["peak_width"][0]),
                T=float(dev["T"][0]), tc=0.7, barriers=barriers)
-    raw["barrier_voltages"] = rng.uniform(-1.0, 3.0, size=B)
+    raw["barrier_voltages"] = rng.uniform(-1.0, 3.0, size=B) + vb_shift
     raw["half"] = float(rng.uniform(1.5, 2.0))
-    raw["centre_offset"] = rng.uniform(-2.0, 2.0, size=n_dot) + offset
+    raw["centre_offset"] = rng.uniform(-spread, spread, size=n_dot) + offset
     raw.update(res=res, pair=pair, vgm_kind=vgm, vc=np.array(vc if vc is not None else (0.0, 0.0)))
     return raw
 

@@ -26,7 +26,8 @@ from oracle import scan as oscan
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CASES = ["ref_4dot_tunnel_identity_vgm", "ref_4dot_tunnel_perfect_vgm_cbb", "ref_5dot_tunnel_low_occupancy",
              "ref_6dot_tunnel_identity_vgm", "ref_8dot_tunnel_identity_vgm", "ref_4dot_constant_tc_no_barriers",
-             "ref_4dot_tunnel_linear_capacitance", "ref_6dot_tunnel_linear_capacitance"]
+             "ref_4dot_tunnel_linear_capacitance", "ref_6dot_tunnel_linear_capacitance",
+             "ref_4dot_tunnel_strong_coupling", "ref_4dot_tunnel_closed_barriers", "ref_6dot_tunnel_far_window"]
 GAP_TOL = 1e-6            # spectral gap below which <n> is not unique
 N_ATOL_CPU = 1e-11        # LAPACK (reference run) vs LAPACK (oracle); measured 5e-14
 N_ATOL_GPU = 2e-6         # Householder + Sturm multisection + inverse iteration on the GPU (tests/test_tunnel_gpu.py)
