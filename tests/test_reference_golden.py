@@ -109,7 +109,8 @@ def test_oracle_matches_reference(name):
     assert ok.mean() > 0.98, f"{(~ok).sum()} degenerate pixels"
     np.testing.assert_allclose(n[ok], d["n"][ok], rtol=0, atol=N_ATOL_CPU)
     np.testing.assert_allclose(z[ok], d["z"][ok], rtol=1e-11, atol=1e-13)
-    assert np.abs(d["n"] - np.rint(d["n"])).max() > 1e-2          # the fixture exercises real tunnel mixing
+    if "closed_barriers" not in name:                             # (that fixture is the t -> 0 limit: integer charges)
+        assert np.abs(d["n"] - np.rint(d["n"])).max() > 1e-2      # the fixture exercises real tunnel mixing
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/qarray_latched"), reason="reference tree not present")
