@@ -40,7 +40,8 @@ CASES = {
     # the env's own regime (env.py:808-858): barriers up to +-15 V from their optimum, i.e. tunnel couplings from 1e-9 to 1e7,
     # and windows tens of volts from the ground truth (occupations of 10-40 carriers on some dots, none on others)
     "ref_4dot_tunnel_strong_coupling": dict(n_dot=4, res=16, seed=19, pair=2, vgm="identity", cbb=False, vb_shift=-8.0),
-    "ref_4dot_tunnel_closed_barriers": dict(n_dot=4, res=16, seed=20, pair=1, vgm="identity", cbb=False, vb_shift=+14.0),
+    "ref_4dot_tunnel_closed_barriers": dict(n_dot=4, res=16, seed=20, pair=1, vgm="identity", cbb=False, vb_shift=+14.0,
+                                            offset=2.5),
     "ref_6dot_tunnel_far_window": dict(n_dot=6, res=10, seed=21, pair=3, vgm="identity", cbb=False, offset=22.0, spread=12.0,
                                        vb_shift=14.0),
 }
