@@ -43,7 +43,7 @@ struct KArgs {
 };
 
 constexpr int QD_DER_DOUBLES = 48;  // derived per-item block: g0[8] gx[8] gy[8] us0 usx usy pad[5] carry[8] + spare
-constexpr int QD_PC_DOUBLES = 8 * 64 + 8 * 16 + 8;   // projection cache: 8 matrices, inversion scratch, keys + meta
+constexpr int QD_PC_DOUBLES = 8 * 64 + 8 * 16 + 8 + 8 * 32;   // projection cache: 8 matrices, inversion scratch, keys + meta; per-lane lin[8]
 
 __host__ __device__ inline int qd_slot_bytes(const qd_layout& L) {
   int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_DER_DOUBLES * 8 + 16;
@@ -96,6 +96,7 @@ __device__ __forceinline__ void matvec_smem(const double* __restrict__ M, const 
   }
 }
 struct ProjCache {
+  double* lin_s;    // [8][32]: per-lane copy of the linear coefficients, indexed by BIT position (free-bit enumeration)
   uint32_t* keys;   // [QD_PC_WAYS]
   uint32_t* meta;   // [0] = entries in use, [1] = next victim
   double* mats;     // [QD_PC_WAYS][64]
@@ -270,6 +271,46 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   }
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   double llo[LOC];
+  double best = INF;
+  int bidx = 0;
+  // ---- (3a) few undecided dots everywhere in the warp: enumerate only those, Gray-code order ----
+  // After (1) and (2) a pixel typically has 0-3 free dots.  E(delta) = sum_j delta_j lin_j + Q[delta] (+ const): walking
+  // the 2^k settings of the free bits in Gray-code order changes one term of the linear part per step and costs one
+  // table look-up.  The winner is the lexicographic (energy, index) minimum = the first minimum of the ascending
+  // enumeration below.  The warp runs 2^kmax steps; wide cases (kmax > 4, or kT > 0) take the block enumeration (3b).
+  const unsigned freeb = ~fixmask & ((1u << N) - 1u);
+  const int kfree = __popc(freeb);
+  const int kmax = __reduce_max_sync(0xffffffffu, kfree);
+  if (kT <= 0.0 && kmax <= 4) {
+    double* __restrict__ ls = pc.lin_s + lane;
+    unsigned idx = fixval, pos = 0;
+    double Lsum = 0.0;
+    {
+      int nfree = 0;
+#pragma unroll
+      for (int p = 0; p < N; ++p) {
+        const double lp = lin[N - 1 - p];
+        ls[p * 32] = lp;
+        if ((fixval >> p) & 1u) Lsum += lp;
+        if ((freeb >> p) & 1u) { pos |= (unsigned)p << (4 * nfree); ++nfree; }
+      }
+    }
+    best = Lsum + Q[idx];
+    bidx = (int)idx;
+    const unsigned steps = 1u << kmax, mine = 1u << kfree;
+#pragma unroll 1
+    for (unsigned c = 1; c < steps; ++c) {
+      if (c < mine) {
+        const unsigned p = (pos >> (4 * (__ffs(c) - 1))) & 15u;
+        idx ^= 1u << p;
+        const double lp = ls[p * 32];
+        Lsum += ((idx >> p) & 1u) ? lp : -lp;
+        const double e = Lsum + Q[idx];
+        if (e < best || (e == best && (int)idx < bidx)) { best = e; bidx = (int)idx; }
+      }
+    }
+  } else {
+  // ---- (3b) block enumeration: low half in registers, high halves on demand ----
   llo[0] = 0.0;
 #pragma unroll
   for (int p = 0; p < NLO; ++p)
@@ -279,7 +320,7 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   for (int b = 0; b < LOC; ++b)
     if (((unsigned)b ^ fixval) & fixmask & (LOC - 1)) llo[b] = INF;
 
-  double best = INF, best_m = INF;
+  double best_m = INF;
   int best_h = 0;
   // high halves H still allowed for this pixel, as a bit set over H; one warp-wide OR gives the H values the warp has
   // to visit at all (a single REDUX instead of a vote per H)
@@ -320,7 +361,7 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
     if (e < best) { best = e; best_m = m; best_h = H; }
   }
   // index of the first candidate of the winning high half that attains the minimum (ascending order, ties -> lowest)
-  int bidx = best_h << NLO;
+  bidx = best_h << NLO;
   {
     const double* __restrict__ q = Q + (best_h << NLO);
     int mb = 0;
@@ -328,6 +369,7 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
     for (int b = LOC - 1; b >= 0; --b)
       if (llo[b] + q[b] == best_m) mb = b;
     bidx |= mb;
+  }
   }
 
   if (kT > 0.0) {
@@ -488,6 +530,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
   pc.aug = pc.mats + 8 * 64;
   pc.keys = reinterpret_cast<uint32_t*>(pc.aug + 8 * 16);
   pc.meta = pc.keys + QD_PC_WAYS;
+  pc.lin_s = pc.aug + 8 * 16 + 8;
 
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
