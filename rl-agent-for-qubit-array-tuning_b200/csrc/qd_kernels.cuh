@@ -218,9 +218,11 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   const double* __restrict__ cinv = rec + L.o_cinv;
   const double* __restrict__ Q = rec + L.o_q;
 
-  bool neg = false;
+  // any g_j < 0?  OR of the sign words (a -0.0 only costs a relax_lcp call that returns at once)
+  int sgn = 0;
 #pragma unroll
-  for (int j = 0; j < N; ++j) neg |= g[j] < 0.0;
+  for (int j = 0; j < N; ++j) sgn |= __double2hiint(g[j]);
+  const bool neg = sgn < 0;
   double nc[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) nc[j] = g[j];
@@ -257,17 +259,17 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   {
     const double* __restrict__ spos = rec + L.o_spos;
     const double* __restrict__ sneg = rec + L.o_sneg;
+    unsigned zmask = 0, omask = 0;
 #pragma unroll
     for (int j = 0; j < N; ++j) {
       const unsigned bit = 1u << (N - 1 - j);
       const double aj = lin[j] + cinv[j * N + j];
-      const bool zero = aj + sneg[j] > 1e-9;
-      const bool one = aj + spos[j] < -1e-9;
-      if (!(fixmask & bit) && (zero || one)) {
-        fixmask |= bit;
-        if (one) fixval |= bit;
-      }
+      zmask |= (aj + sneg[j] > 1e-9) ? bit : 0u;
+      omask |= (aj + spos[j] < -1e-9) ? bit : 0u;
     }
+    const unsigned add = (zmask | omask) & ~fixmask;       // thresholded bits keep their own value
+    fixval |= omask & add;
+    fixmask |= add;
   }
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   double llo[LOC];
