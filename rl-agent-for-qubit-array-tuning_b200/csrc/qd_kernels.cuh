@@ -166,7 +166,7 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
                                           int lane, double (&nc)[N]) {
   unsigned act = 0;
 #pragma unroll
-  for (int j = 0; j < N; ++j) act |= (g[j] < 0.0) ? (1u << j) : 0u;
+  for (int j = 0; j < N; ++j) act |= ((unsigned)__double2hiint(g[j]) >> 31) << j;     // sign bits (a -0.0 clamps to 0 too)
   bool need = act != 0;
 #pragma unroll
   for (int j = 0; j < N; ++j) nc[j] = g[j];
@@ -192,7 +192,7 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
         for (int i = 0; i < N; ++i) {
           const double sacc = ((act >> i) & 1u) ? 0.0 : wv[i];
           nc[i] = sacc;
-          neu |= (sacc < 0.0) ? (1u << i) : 0u;
+          neu |= ((unsigned)__double2hiint(sacc) >> 31) << i;
         }
         changed = neu != act;
         act = neu;
@@ -201,8 +201,7 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
     }
     need = changed;
   }
-#pragma unroll
-  for (int j = 0; j < N; ++j) nc[j] = fmax(nc[j], 0.0);
+  // (a lane leaves the loop only after a round that produced no negative entry, so nc >= 0 here)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
