@@ -43,7 +43,7 @@ struct KArgs {
 };
 
 constexpr int QD_DER_DOUBLES = 48;  // derived per-item block: g0[8] gx[8] gy[8] us0 usx usy pad[5] carry[8] + spare
-constexpr int QD_PC_DOUBLES = 8 * 64 + 8 * 16 + 8 + 8 * 32;   // projection cache: 8 matrices, inversion scratch, keys + meta; per-lane lin[8]
+constexpr int QD_PC_DOUBLES = 8 * 64 + 8 * 16 + 8 + 8 * 32 + 8 * 24;   // projection cache: 8 matrices, inversion scratch, keys + meta; per-lane lin[8]; affine forms
 
 __host__ __device__ inline int qd_slot_bytes(const qd_layout& L) {
   int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_DER_DOUBLES * 8 + 16;
@@ -96,6 +96,8 @@ __device__ __forceinline__ void matvec_smem(const double* __restrict__ M, const 
   }
 }
 struct ProjCache {
+  double* aff;      // [QD_PC_WAYS][3][8]: P_S g0, P_S gx, P_S gy -- the relaxed occupations are affine in the pixel indices
+  const double* gsrc;  // g0[8] gx[8] gy[8] of the current item (nullptr: explicit voltage list, no affine form)
   double* lin_s;    // [8][32]: per-lane copy of the linear coefficients, indexed by BIT position (free-bit enumeration)
   uint32_t* keys;   // [QD_PC_WAYS]
   uint32_t* meta;   // [0] = entries in use, [1] = next victim
@@ -152,6 +154,18 @@ __device__ __noinline__ int proj_cache_build(const ProjCache& pc, const double* 
     if ((S >> i) & 1u) v = 0.0;
     P[e] = v;
   }
+  __syncwarp();
+  if (pc.gsrc != nullptr && lane < 24) {
+    // g = g0 + ix gx + iy gy on an affine scan, so w = P_S g = (P_S g0) + ix (P_S gx) + iy (P_S gy): three small
+    // mat-vecs per (item, S) replace one per pixel and round
+    const int t = lane >> 3, i = lane & 7;
+    double acc = 0.0;
+    if (i < N) {
+      const double* src = pc.gsrc + 8 * t;
+      for (int j = 0; j < N; ++j) acc = fma(P[i * N + j], src[j], acc);
+    }
+    pc.aff[slot * 24 + lane] = acc;
+  }
   if (lane == 0) {
     pc.keys[slot] = S;
     pc.meta[1] = (uint32_t)((slot + 1) % QD_PC_WAYS);
@@ -163,7 +177,7 @@ __device__ __noinline__ int proj_cache_build(const ProjCache& pc, const double* 
 
 template <int N>
 __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __restrict__ cdd, const ProjCache& pc,
-                                          int lane, double (&nc)[N]) {
+                                          int lane, double fx, double fy, double (&nc)[N]) {
   unsigned act = 0;
 #pragma unroll
   for (int j = 0; j < N; ++j) act |= ((unsigned)__double2hiint(g[j]) >> 31) << j;     // sign bits (a -0.0 clamps to 0 too)
@@ -187,7 +201,24 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
         const double* __restrict__ P = pc.mats + slot * 64;
         unsigned neu = act;
         double wv[N];
-        matvec_smem<N>(P, g, wv);
+        if (pc.gsrc != nullptr) {
+          const double* __restrict__ A = pc.aff + slot * 24;
+          if constexpr (N % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i += 2) {
+              const double2 a0 = *reinterpret_cast<const double2*>(A + i);
+              const double2 ax = *reinterpret_cast<const double2*>(A + 8 + i);
+              const double2 ay = *reinterpret_cast<const double2*>(A + 16 + i);
+              wv[i] = fma(fy, ay.x, fma(fx, ax.x, a0.x));
+              wv[i + 1] = fma(fy, ay.y, fma(fx, ax.y, a0.y));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) wv[i] = fma(fy, A[16 + i], fma(fx, A[8 + i], A[i]));
+          }
+        } else {
+          matvec_smem<N>(P, g, wv);
+        }
 #pragma unroll
         for (int i = 0; i < N; ++i) {
           const double sacc = ((act >> i) & 1u) ? 0.0 : wv[i];
@@ -210,7 +241,7 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
 template <int N>
 __device__ __forceinline__ void ground_state_box(const double (&g)[N], const double* __restrict__ rec,
                                                  const qd_layout& L, const ProjCache& pc, int lane, bool thresholded,
-                                                 double kT, double (&nd)[N]) {
+                                                 double kT, double fx, double fy, double (&nd)[N]) {
   constexpr int NLO = N < 4 ? N : 4;
   constexpr int NHI = N - NLO;
   constexpr int LOC = 1 << NLO;
@@ -225,7 +256,7 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   double nc[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) nc[j] = g[j];
-  if (__any_sync(0xffffffffu, neg)) relax_lcp<N>(g, rec + L.o_cdd, pc, lane, nc);
+  if (__any_sync(0xffffffffu, neg)) relax_lcp<N>(g, rec + L.o_cdd, pc, lane, fx, fy, nc);
 
   double f[N], r[N], lin[N];
 #pragma unroll
@@ -500,10 +531,15 @@ __device__ __forceinline__ uint32_t compose2(uint32_t later, uint32_t earlier) {
 }
 
 template <int N>
-__device__ __forceinline__ uint64_t pack_key(const double (&nd)[N]) {
+__device__ __forceinline__ uint64_t pack_key(const double (&nd)[N], bool integral) {
   uint64_t k = 0;
+  if (integral) {                                  // hard argmin (kT == 0): the occupations are exact integers
 #pragma unroll
-  for (int j = 0; j < N; ++j) k |= (uint64_t)((unsigned)(int)floor(nd[j] + 0.5) & 0xffu) << (8 * j);
+    for (int j = 0; j < N; ++j) k |= (uint64_t)((unsigned)__double2int_rz(nd[j]) & 0xffu) << (8 * j);
+  } else {
+#pragma unroll
+    for (int j = 0; j < N; ++j) k |= (uint64_t)((unsigned)(int)floor(nd[j] + 0.5) & 0xffu) << (8 * j);
+  }
   return k;
 }
 
@@ -532,6 +568,8 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
   pc.keys = reinterpret_cast<uint32_t*>(pc.aug + 8 * 16);
   pc.meta = pc.keys + QD_PC_WAYS;
   pc.lin_s = pc.aug + 8 * 16 + 8;
+  pc.aff = pc.lin_s + 8 * 32;
+  pc.gsrc = (a.points == nullptr) ? der : nullptr;
 
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
@@ -652,11 +690,11 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
 #pragma unroll
             for (int j = 0; j < N; ++j) nd[j] = src[j];
           } else if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N>(g, rec, L, kT, nd);
-          else ground_state_box<N>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, nd);
+          else ground_state_box<N>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, (double)ixc, (double)iy, nd);
 
           // ---- hysteresis latching along x ----
           if (latch_on) {
-            uint64_t key = pack_key<N>(nd);
+            uint64_t key = pack_key<N>(nd, ALG != QD_ALG_TUNNEL && kT <= 0.0);
             unsigned todo = vmask;
             if (!have_held) {                       // first pixel of the row (or of the scan): accepted as is
               held_key = shfl_u64(key, 0);
