@@ -694,7 +694,11 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
 
           // ---- hysteresis latching along x ----
           if (latch_on) {
-            uint64_t key = pack_key<N>(nd, ALG != QD_ALG_TUNNEL && kT <= 0.0);
+            // integral: hard argmin, the occupations ARE the key bytes -- the event loop then works on keys alone
+            // and the occupations of the latched pixels are unpacked once at the end
+            const bool integral = ALG != QD_ALG_TUNNEL && kT <= 0.0;
+            uint64_t key = pack_key<N>(nd, integral);
+            const uint64_t key_free = key;
             unsigned todo = vmask;
             if (!have_held) {                       // first pixel of the row (or of the scan): accepted as is
               held_key = shfl_u64(key, 0);
@@ -727,12 +731,14 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
               const int a = acc ? __ffs(acc) - 1 : 32;       // accepting pixel (32: nobody in this run)
               const unsigned rejected = run & ((a >= 32) ? ~0u : ((1u << a) - 1u));
               if (rejected) {
-                const int src = (i > 0) ? i - 1 : 0;
+                if (!integral) {
+                  const int src = (i > 0) ? i - 1 : 0;
 #pragma unroll
-                for (int j = 0; j < N; ++j) {
-                  const double prev = shfl_f64(nd[j], src);
-                  const double held = (i > 0) ? prev : d_carry[j];
-                  if ((rejected >> lane) & 1u) nd[j] = held;
+                  for (int j = 0; j < N; ++j) {
+                    const double prev = shfl_f64(nd[j], src);
+                    const double held = (i > 0) ? prev : d_carry[j];
+                    if ((rejected >> lane) & 1u) nd[j] = held;
+                  }
                 }
                 if ((rejected >> lane) & 1u) key = held_key;
               }
@@ -740,13 +746,20 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
               const int done_to = (a < 32) ? a : (31 - __clz(run));
               todo &= ~((2u << done_to) - 1u);
             }
-            // configuration after the last valid pixel -> carry for the next chunk
-            const int last = 31 - __clz(vmask);
-            if (lane == last) {
+            if (integral) {
+              if (key != key_free) {
 #pragma unroll
-              for (int j = 0; j < N; ++j) d_carry[j] = nd[j];
+                for (int j = 0; j < N; ++j) nd[j] = (double)(int)((unsigned)(key >> (8 * j)) & 0xffu);
+              }
+            } else {
+              // configuration after the last valid pixel -> carry for the next chunk
+              const int last = 31 - __clz(vmask);
+              if (lane == last) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) d_carry[j] = nd[j];
+              }
+              __syncwarp();
             }
-            __syncwarp();
           }
 
           // ---- sensor input noise: white + telegraph ----
