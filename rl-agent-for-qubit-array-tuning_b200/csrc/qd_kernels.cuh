@@ -13,11 +13,12 @@
 //
 // Candidate search without the O(N^2) quadratic form per candidate.  With r = floor(n_c) - g and h = Cinv r,
 //     E(delta) = (r+delta)^T Cinv (r+delta) = r.h + sum_j delta_j 2 h_j + Q[delta],   Q[delta] = delta^T Cinv delta.
-//   Q depends on the env only: 2^N doubles precomputed at qd_set_models and staged with the record.  The linear part
-//   splits over the low/high halves of the bit string: L(delta) = Lhi[H] + Llo[b]; Llo (<=16 values) lives in
-//   registers.  Per candidate the inner loop is one broadcast LDS (shared by two candidates), one DADD and one
-//   compare/select; per H one more DADD + compare.  Enumeration order = ascending index, dot 0 most significant,
-//   strict '<' so the first minimum wins (oracle/path_a.py).
+//   Q depends on the env only: 2^N doubles precomputed at qd_set_models and staged with the record.  Exact dominance
+//   bounds fix most dots first (ground_state_box, step 2); the 0-3 undecided ones are walked in Gray-code order (one
+//   term of the linear part and one Q look-up per step, step 3a).  Wide cases and kT > 0 use the block enumeration
+//   (3b): the linear part splits over the low/high halves of the bit string, L(delta) = Lhi[H] + Llo[b], Llo (<= 16
+//   values) in registers, one broadcast LDS per two candidates.  Either way the winner is the first minimum of the
+//   ascending enumeration (dot 0 most significant), as in oracle/path_a.py.
 #pragma once
 #include <math.h>
 

@@ -3,17 +3,23 @@
 // the 32-state truncated basis maps one basis state to one lane.
 //
 // Per pixel (all 32 lanes cooperate):
-//   1. dot potentials g = cgd[:N] v, continuous relaxation (closed form, or the reference's 50 projected-gradient steps).
+//   1. dot potentials g = cgd[:N] v (scaled per pixel when the linear voltage-dependent capacitance model is on),
+//      continuous relaxation: closed form, or the reference's 50 projected-gradient steps (in registers: lane 4i + p
+//      owns two columns of row i, a 4-lane butterfly per step).
 //   2. 4^N candidates floor(n_c) + {-1,0,1,2}^N.  E = z^T C z, z = r + delta.  The digits split into a high and a low
-//      half (<= 256 combinations each).  A block = one high combination: its 256 low candidates cost ~8 instructions
-//      each (table of the low quadratic part + 4 FMA of the block-dependent linear part).  Blocks are visited in
-//      increasing order of the Schur-complement lower bound  z_hi^T (Chh - Chl Cll^-1 Clh) z_hi  and the walk stops
-//      when the bound exceeds the current 32nd-best energy: exact, typically 5-20 of 256 blocks at N = 8.
-//      The running top-32 lives one entry per lane; selection order is (energy, index) = the reference's stable sort.
+//      half (<= 256 combinations each; the most deeply empty dots go to the high half, chosen per work item).  A block
+//      = one high combination.  Blocks are visited in increasing order of the Schur-complement lower bound
+//      z_hi^T (Chh - Chl Cll^-1 Clh) z_hi and the walk stops when the bound exceeds the current 32nd-best energy: exact.
+//      The running top-32 lives sorted across the lanes, ordered by (energy, index) = the reference's stable sort; it is
+//      WARM-STARTED from the previous pixel's basis (re-evaluated with the same arithmetic, bitonic-sorted), so the walk
+//      only inserts the newcomers.
 //   3. H = diag(F) + nearest-neighbour hopping -t_d sqrt(n_from (n_to + 1)), t_d = tc_base exp(-alpha_d vb_eff_d).
-//   4. Ground eigenvector: Householder tridiagonalisation in shared memory (lane = row), lowest eigenvalue bracketed by
-//      32-way multisection on Sturm counts (each lane one shift), inverse iteration on the tridiagonal with the shift
-//      at the lower bracket end (T - mu I is positive definite there: LDL^T without pivoting), back-transformation.
+//      Hopping conserves the total charge: the lanes are sorted by (total charge, lane), H is block diagonal, and every
+//      dense step below runs on all SECTORS at once, each in its own lane segment (segmented shuffle scans).
+//   4. Ground eigenvector: Householder tridiagonalisation in shared memory (lane = row, largest sector - 2 steps),
+//      lowest eigenvalue bracketed by 32-way multisection -- x < lambda_0 iff every leading principal minor of
+//      T - x I is positive, on the tridiagonal mapped to [0, 1] -- then per sector LDL^T (T - mu I is positive definite
+//      at the lower bracket end: no pivoting) and inverse iteration by the sector's leader lane, back-transformation.
 //   5. <n> = sum_m psi_m^2 n_m is written to a scratch buffer; latching, sensor and noise are then applied by
 //      qd_scan_kernel<N, QD_ALG_TUNNEL> (lane per pixel), so a flat latching pass never serialises the eigen-solves.
 #pragma once
