@@ -72,3 +72,46 @@ def time_scans(mb, scans, flags: int, threads: int = 0):
     _, _, dt = run_scans(mb, scans, flags, threads=threads, want_n=False)
     pixels = int((scans["nx"].astype(np.int64) * scans["ny"]).sum())
     return pixels / dt, pixels, dt
+
+
+# ---- Path B (tunnel-coupled ground state): oracle/cport/qd_cport_b.c ----------------------------------------------------
+_SRC_B = os.path.join(_HERE, "qd_cport_b.c")
+_LIB_B = os.path.join(_HERE, "libqd_cport_b.so")
+_lib_b = None
+
+
+def _load_b():
+    global _lib_b
+    if _lib_b is None:
+        if not os.path.exists(_LIB_B) or os.path.getmtime(_LIB_B) < os.path.getmtime(_SRC_B):
+            subprocess.check_call(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-o", _LIB_B, _SRC_B, "-lm"])
+        lib = C.CDLL(_LIB_B)
+        vp = C.c_void_p
+        lib.qd_cport_tunnel_points.argtypes = [C.c_long, C.c_int, C.c_int, C.c_int, vp, vp, vp, C.c_double, vp, C.c_double,
+                                               C.c_double, vp, vp, vp, C.c_int]
+        lib.qd_cport_tunnel_points.restype = C.c_int
+        _lib_b = lib
+    return _lib_b
+
+
+def tunnel_ground_state(m, v_ext, threads: int = 1):
+    """``m``: oracle.scan.Model (algorithm "tunnel"); ``v_ext`` (P, n_volt).  Returns (<n> (P, N), gap (P,), seconds):
+    the reference's formulation in C (all 4^N candidates, 32 x 32 Jacobi), OpenMP over pixels."""
+    lib = _load_b()
+    v = np.ascontiguousarray(v_ext, dtype=np.float64)
+    cinv = np.ascontiguousarray(m.cdd_inv, dtype=np.float64)
+    a = np.ascontiguousarray(m.cgd, dtype=np.float64)
+    n, nv = cinv.shape[0], a.shape[1]
+    cbg = None if m.cbg is None or nv <= m.n_gate else np.ascontiguousarray(m.cbg, dtype=np.float64)
+    alpha = np.ascontiguousarray(np.asarray(m.alpha, dtype=np.float64) if m.alpha is not None else np.zeros(8))
+    out = np.empty((v.shape[0], n))
+    gap = np.empty(v.shape[0])
+    t0 = time.perf_counter()
+    rc = lib.qd_cport_tunnel_points(v.shape[0], n, nv, m.n_gate, cinv.ctypes.data, a.ctypes.data,
+                                    None if cbg is None else cbg.ctypes.data, float(m.tc_base), alpha.ctypes.data,
+                                    float(getattr(m, "vc_alpha", 0.0)), float(getattr(m, "vc_beta", 0.0)), v.ctypes.data,
+                                    out.ctypes.data, gap.ctypes.data, int(threads))
+    dt = time.perf_counter() - t0
+    if rc != 0:
+        raise RuntimeError(f"qd_cport_tunnel_points failed: {rc}")
+    return out, gap, dt
