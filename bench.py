@@ -226,15 +226,18 @@ def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_e
         from oracle import composer, cport
         from util import oracle_model, oracle_scan
         cores = os.cpu_count() or 1
-        m = oracle_model(mb, int(scans[0]["env_id"]), 0)
-        s0 = oracle_scan(scans[0], mb.n_volt, 0)
-        v = composer.affine_grid(s0.v0, s0.dx, s0.dy, s0.nx, s0.ny).reshape(-1, mb.n_volt)
+        m = oracle_model(mb, 0, 0)
+        grids = []
+        for rec in scans[scans["env_id"] == 0]:              # every window of env 0 (N-1 scans)
+            s0 = oracle_scan(rec, mb.n_volt, 0)
+            grids.append(composer.affine_grid(s0.v0, s0.dx, s0.dy, s0.nx, s0.ny).reshape(-1, mb.n_volt))
+        v = np.concatenate(grids)
         cal = v[: 8 * cores]
         _, _, dt = cport.tunnel_ground_state(m, cal, threads=cores)
         n_pix = int(min(len(v), max(len(cal), 8.0 * len(cal) / max(dt, 1e-6))))        # about 8 s of CPU work
         _, _, dt = cport.tunnel_ground_state(m, v[:n_pix], threads=cores)
         blk["cpu_baseline"] = {"value": n_pix / dt, "unit": "pixels/s", "cores": cores, "kind": "port",
-                               "sample": f"{n_pix} pixels of one scan window (ground state only), {dt:.1f} s",
+                               "sample": f"{n_pix} pixels of one env's scan windows (ground state only), {dt:.1f} s",
                                "what": "plain-C restatement of qarray_latched._ground_state_open in the reference's "
                                        "formulation, OpenMP over pixels"}
     return blk
