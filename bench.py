@@ -183,6 +183,29 @@ def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int, pat
     return dev, mb, sets
 
 
+def tunnel_cpu_baseline(mb, scans, budget_s: float = 8.0):
+    """The tunnel path's reference formulation in plain C (all 4^N candidates as full quadratic forms, 32 x 32
+    eigen-solve; oracle/cport/qd_cport_b.c, checked against the reference-made fixtures in tests/), OpenMP over the pixels
+    of env 0's scan windows on every host core, about ``budget_s`` seconds."""
+    from oracle import composer, cport
+    from util import oracle_model, oracle_scan
+    cores = os.cpu_count() or 1
+    m = oracle_model(mb, 0, 0)
+    grids = []
+    for rec in scans[scans["env_id"] == 0]:              # every window of env 0 (N-1 scans)
+        s0 = oracle_scan(rec, mb.n_volt, 0)
+        grids.append(composer.affine_grid(s0.v0, s0.dx, s0.dy, s0.nx, s0.ny).reshape(-1, mb.n_volt))
+    v = np.concatenate(grids)
+    cal = v[: 8 * cores]
+    _, _, dt = cport.tunnel_ground_state(m, cal, threads=cores)
+    n_pix = int(min(len(v), max(len(cal), budget_s * len(cal) / max(dt, 1e-6))))
+    _, _, dt = cport.tunnel_ground_state(m, v[:n_pix], threads=cores)
+    return {"value": n_pix / dt, "unit": "pixels/s", "cores": cores, "kind": "port",
+            "sample": f"{n_pix} pixels of one env's scan windows (ground state only), {dt:.1f} s",
+            "what": "plain-C restatement of qarray_latched._ground_state_open in the reference's formulation, "
+                    "OpenMP over pixels"}
+
+
 def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_env: int = 512):
     """Path B on the same GPU: n_env envs of the n_dot tunnel-coupled array, device-resident, CUDA events; the NumPy
     restatement (pinned against the reference itself, tests/test_reference_golden.py) timed on a small sample."""
@@ -221,25 +244,7 @@ def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_e
                                  "achieved": blk["value"] * instr, "peak": peak, "unit": "warp-instr/s",
                                  "frac": blk["value"] * instr / peak}
     if with_cpu:
-        # the reference formulation in plain C (all 4^N candidates as full quadratic forms, 32 x 32 eigen-solve), OpenMP
-        # over the pixels of one window on every host core; checked against the reference-made fixtures in tests/
-        from oracle import composer, cport
-        from util import oracle_model, oracle_scan
-        cores = os.cpu_count() or 1
-        m = oracle_model(mb, 0, 0)
-        grids = []
-        for rec in scans[scans["env_id"] == 0]:              # every window of env 0 (N-1 scans)
-            s0 = oracle_scan(rec, mb.n_volt, 0)
-            grids.append(composer.affine_grid(s0.v0, s0.dx, s0.dy, s0.nx, s0.ny).reshape(-1, mb.n_volt))
-        v = np.concatenate(grids)
-        cal = v[: 8 * cores]
-        _, _, dt = cport.tunnel_ground_state(m, cal, threads=cores)
-        n_pix = int(min(len(v), max(len(cal), 8.0 * len(cal) / max(dt, 1e-6))))        # about 8 s of CPU work
-        _, _, dt = cport.tunnel_ground_state(m, v[:n_pix], threads=cores)
-        blk["cpu_baseline"] = {"value": n_pix / dt, "unit": "pixels/s", "cores": cores, "kind": "port",
-                               "sample": f"{n_pix} pixels of one env's scan windows (ground state only), {dt:.1f} s",
-                               "what": "plain-C restatement of qarray_latched._ground_state_open in the reference's "
-                                       "formulation, OpenMP over pixels"}
+        blk["cpu_baseline"] = tunnel_cpu_baseline(mb, scans)
     return blk
 
 

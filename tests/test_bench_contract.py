@@ -34,3 +34,14 @@ def test_flop_models_match_the_survey_figures():
     import bench
     assert [bench.flops_reference_formulation(n) for n in (2, 4, 6, 8)] == [402.0, 1450.0, 6850.0, 39210.0]
     assert bench.flops_factored(8) < bench.flops_reference_formulation(8) / 30
+
+
+def test_tunnel_cpu_baseline_block():
+    """The CPU comparator of bench.py's tunnel-path block runs on its own (no GPU) and reports the contract's keys."""
+    import bench
+    from qdsim import synth
+    dev = synth.sample_barrier_devices(2, 4, seed=3)
+    mb = synth.tunnel_batch(dev)
+    scans = synth.env_step_scans(mb, dev, res=8, seed=4)
+    out = bench.tunnel_cpu_baseline(mb, scans, budget_s=0.2)
+    assert out["kind"] == "port" and out["unit"] == "pixels/s" and out["value"] > 0 and out["cores"] >= 1
