@@ -239,7 +239,7 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
 // ---------------------------------------------------------------------------------------------------------------
 // default / thresholded ground state of one pixel.  nd[] <- occupations (integers when kT == 0).
 // ---------------------------------------------------------------------------------------------------------------
-template <int N>
+template <int N, bool THERMAL>
 __device__ __forceinline__ void ground_state_box(const double (&g)[N], const double* __restrict__ rec,
                                                  const qd_layout& L, const ProjCache& pc, int lane, bool thresholded,
                                                  double kT, double fx, double fy, double (&nd)[N]) {
@@ -310,11 +310,11 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   // After (1) and (2) a pixel typically has 0-3 free dots.  E(delta) = sum_j delta_j lin_j + Q[delta] (+ const): walking
   // the 2^k settings of the free bits in Gray-code order changes one term of the linear part per step and costs one
   // table look-up.  The winner is the lexicographic (energy, index) minimum = the first minimum of the ascending
-  // enumeration below.  The warp runs 2^kmax steps; wide cases (kmax > 4, or kT > 0) take the block enumeration (3b).
+  // enumeration below.  The warp runs 2^kmax steps; wide cases (kmax > 4) take the block enumeration (3b).
   const unsigned freeb = ~fixmask & ((1u << N) - 1u);
   const int kfree = __popc(freeb);
   const int kmax = __reduce_max_sync(0xffffffffu, kfree);
-  if (kT <= 0.0 && kmax <= 4) {
+  if (kmax <= 4) {
     double* __restrict__ ls = pc.lin_s + lane;
     unsigned idx = fixval, pos = 0;
     double Lsum = 0.0;
@@ -405,14 +405,75 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   }
   }
 
-  if (kT > 0.0) {
+  if (THERMAL && kT > 0.0) {
     // Boltzmann average over the same candidates, weights exp(-(E - Emin)/kT)
     const double inv_kT = 1.0 / kT;
     double Z = 0.0;
     double acc[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) acc[j] = 0.0;
-    // every candidate the algorithm allows carries weight: drop the dominance restrictions, keep the thresholded ones
+    // Every candidate the algorithm allows carries weight exp(-(E - Emin)/kT), cut at 40 kT (4e-18).  A dot whose flip
+    // costs more than that cut-off whatever the others do (the dominance bounds of step 2 with margin 40 kT) has one
+    // value in every candidate that survives the cut, so only the remaining dots are walked (Gray code, as in 3a).
+    const double cut = 40.0 * kT;
+    unsigned tmask = thr_mask, tval = thr_val;
+    {
+      const double* __restrict__ spos = rec + L.o_spos;
+      const double* __restrict__ sneg = rec + L.o_sneg;
+      unsigned zt = 0, ot = 0;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const unsigned bit = 1u << (N - 1 - j);
+        const double aj = lin[j] + cinv[j * N + j];
+        zt |= (aj + sneg[j] > cut) ? bit : 0u;
+        ot |= (aj + spos[j] < -cut) ? bit : 0u;
+      }
+      const unsigned add = (zt | ot) & ~tmask;
+      tval |= ot & add;
+      tmask |= add;
+    }
+    const unsigned freet = ~tmask & ((1u << N) - 1u);
+    const int kft = __popc(freet);
+    const int kmt = __reduce_max_sync(0xffffffffu, kft);
+    if (kmt <= 6) {
+      double* __restrict__ ls = pc.lin_s + lane;
+      unsigned idx = tval, pos = 0;
+      double Lsum = 0.0, Z = 0.0;
+      {
+        int nfree = 0;
+#pragma unroll
+        for (int p = 0; p < N; ++p) {
+          const double lp = lin[N - 1 - p];
+          ls[p * 32] = lp;
+          if ((tval >> p) & 1u) Lsum += lp;
+          if ((freet >> p) & 1u) { pos |= (unsigned)p << (4 * nfree); ++nfree; }
+        }
+      }
+      const unsigned steps = 1u << kmt, mine = 1u << kft;
+#pragma unroll 1
+      for (unsigned c = 0; c < steps; ++c) {
+        if (c < mine) {
+          if (c > 0) {
+            const unsigned p = (pos >> (4 * (__ffs(c) - 1))) & 15u;
+            idx ^= 1u << p;
+            const double lp = ls[p * 32];
+            Lsum += ((idx >> p) & 1u) ? lp : -lp;
+          }
+          const double d = ((Lsum + Q[idx]) - best) * inv_kT;
+          if (d < 40.0) {
+            const double wgt = exp(-d);
+            Z += wgt;
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+              if ((idx >> (N - 1 - j)) & 1u) acc[j] += wgt;
+          }
+        }
+      }
+      const double invZ = 1.0 / Z;
+#pragma unroll
+      for (int j = 0; j < N; ++j) nd[j] = f[j] + acc[j] * invZ;
+      return;
+    }
     llo[0] = 0.0;
 #pragma unroll
     for (int p = 0; p < NLO; ++p)
@@ -500,7 +561,7 @@ struct BruteLevel<N, N> {
                                              double&, unsigned&, double, double&, double (&)[N]) {}
 };
 
-template <int N>
+template <int N, bool THERMAL>
 __device__ __forceinline__ void ground_state_brute(const double (&g)[N], const double* __restrict__ rec,
                                                    const qd_layout& L, double kT, double (&nd)[N]) {
   const double* __restrict__ cinv = rec + L.o_cinv;
@@ -512,7 +573,7 @@ __device__ __forceinline__ void ground_state_brute(const double (&g)[N], const d
 #pragma unroll
   for (int j = 0; j < N; ++j) { t[j] = 0.0; acc[j] = 0.0; }
   BruteLevel<N, 0>::template run<0>(cinv, g, maxc, 0.0, t, 0u, best, bcode, 0.0, Z, acc);
-  if (kT > 0.0) {
+  if (THERMAL && kT > 0.0) {
     BruteLevel<N, 0>::template run<1>(cinv, g, maxc, 0.0, t, 0u, best, bcode, 1.0 / kT, Z, acc);
     const double invZ = 1.0 / Z;
 #pragma unroll
@@ -544,7 +605,9 @@ __device__ __forceinline__ uint64_t pack_key(const double (&nd)[N], bool integra
   return k;
 }
 
-template <int N, int ALG>
+// THERMAL = false instantiations carry no Boltzmann-average code at all (the hard-argmin kernels are the hot ones; the
+// launch picks THERMAL = true only when QD_FLAG_THERMAL is set).
+template <int N, int ALG, bool THERMAL>
 __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs a) {
   extern __shared__ __align__(128) unsigned char qd_smem[];
   const int lane = threadIdx.x & 31;
@@ -628,7 +691,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
     __syncwarp();
 
     const double* par = rec + L.o_par;
-    const double kT = f_thermal ? par[QD_PAR_KT] : 0.0;
+    const double kT = (THERMAL && f_thermal) ? par[QD_PAR_KT] : 0.0;
     const bool latch_on = f_latch && par[QD_PAR_LATCH] != 0.0;
     const bool replace = f_radial && sc->rad_mode == 2;
     const uint64_t seed = sc->seed;
@@ -690,8 +753,8 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
             const double* __restrict__ src = a.nbar + (size_t)(pix0 + pix) * N;
 #pragma unroll
             for (int j = 0; j < N; ++j) nd[j] = src[j];
-          } else if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N>(g, rec, L, kT, nd);
-          else ground_state_box<N>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, (double)ixc, (double)iy, nd);
+          } else if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N, THERMAL>(g, rec, L, kT, nd);
+          else ground_state_box<N, THERMAL>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, (double)ixc, (double)iy, nd);
 
           // ---- hysteresis latching along x ----
           if (latch_on) {
