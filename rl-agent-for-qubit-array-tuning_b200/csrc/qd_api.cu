@@ -94,17 +94,17 @@ size_t n_elem_size(int n_type) {
 
 using kernel_fn = void (*)(const qd::KArgs);
 
-template <int ALG, bool THERMAL>
+template <int ALG, bool THERMAL, bool POINTS>
 kernel_fn pick_n(int n) {
   switch (n) {
-    case 1: return qd::qd_scan_kernel<1, ALG, THERMAL>;
-    case 2: return qd::qd_scan_kernel<2, ALG, THERMAL>;
-    case 3: return qd::qd_scan_kernel<3, ALG, THERMAL>;
-    case 4: return qd::qd_scan_kernel<4, ALG, THERMAL>;
-    case 5: return qd::qd_scan_kernel<5, ALG, THERMAL>;
-    case 6: return qd::qd_scan_kernel<6, ALG, THERMAL>;
-    case 7: return qd::qd_scan_kernel<7, ALG, THERMAL>;
-    case 8: return qd::qd_scan_kernel<8, ALG, THERMAL>;
+    case 1: return qd::qd_scan_kernel<1, ALG, THERMAL, POINTS>;
+    case 2: return qd::qd_scan_kernel<2, ALG, THERMAL, POINTS>;
+    case 3: return qd::qd_scan_kernel<3, ALG, THERMAL, POINTS>;
+    case 4: return qd::qd_scan_kernel<4, ALG, THERMAL, POINTS>;
+    case 5: return qd::qd_scan_kernel<5, ALG, THERMAL, POINTS>;
+    case 6: return qd::qd_scan_kernel<6, ALG, THERMAL, POINTS>;
+    case 7: return qd::qd_scan_kernel<7, ALG, THERMAL, POINTS>;
+    case 8: return qd::qd_scan_kernel<8, ALG, THERMAL, POINTS>;
     default: return nullptr;
   }
 }
@@ -122,13 +122,16 @@ kernel_fn pick_tunnel_gs(int n) {
   }
 }
 
-kernel_fn pick_kernel(const qd_layout& L, unsigned flags) {
+template <int ALG, bool THERMAL>
+kernel_fn pick_p(int n, bool points) { return points ? pick_n<ALG, THERMAL, true>(n) : pick_n<ALG, THERMAL, false>(n); }
+
+kernel_fn pick_kernel(const qd_layout& L, unsigned flags, bool points) {
   const bool thermal = flags & QD_FLAG_THERMAL;
-  if (L.algorithm == QD_ALG_TUNNEL) return pick_n<QD_ALG_TUNNEL, false>(L.n_dot);
+  if (L.algorithm == QD_ALG_TUNNEL) return pick_p<QD_ALG_TUNNEL, false>(L.n_dot, points);
   if (L.algorithm == QD_ALG_BRUTE_FORCE)
-    return thermal ? pick_n<QD_ALG_BRUTE_FORCE, true>(L.n_dot) : pick_n<QD_ALG_BRUTE_FORCE, false>(L.n_dot);
+    return thermal ? pick_p<QD_ALG_BRUTE_FORCE, true>(L.n_dot, points) : pick_p<QD_ALG_BRUTE_FORCE, false>(L.n_dot, points);
   if (L.algorithm == QD_ALG_DEFAULT || L.algorithm == QD_ALG_THRESHOLDED)
-    return thermal ? pick_n<QD_ALG_DEFAULT, true>(L.n_dot) : pick_n<QD_ALG_DEFAULT, false>(L.n_dot);
+    return thermal ? pick_p<QD_ALG_DEFAULT, true>(L.n_dot, points) : pick_p<QD_ALG_DEFAULT, false>(L.n_dot, points);
   return nullptr;
 }
 
@@ -147,7 +150,7 @@ int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) 
 // enqueue one launch over device-resident descriptors
 int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const double* d_points, float* d_z, void* d_n,
            int n_type, unsigned flags, cudaStream_t stream, int rows_cap = 0) {
-  kernel_fn fn = pick_kernel(ctx->L, flags);
+  kernel_fn fn = pick_kernel(ctx->L, flags, d_points != nullptr);
   if (!fn) return fail(ctx, QD_ERR_UNSUPPORTED, "no kernel for n_dot=%d algorithm=%d", ctx->L.n_dot, ctx->L.algorithm);
   qd::KArgs a;
   a.nbar = nullptr;

@@ -176,7 +176,7 @@ __device__ __noinline__ int proj_cache_build(const ProjCache& pc, const double* 
   return slot;
 }
 
-template <int N>
+template <int N, bool AFFINE>
 __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __restrict__ cdd, const ProjCache& pc,
                                           int lane, double fx, double fy, double (&nc)[N]) {
   unsigned act = 0;
@@ -202,7 +202,7 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
         const double* __restrict__ P = pc.mats + slot * 64;
         unsigned neu = act;
         double wv[N];
-        if (pc.gsrc != nullptr) {
+        if constexpr (AFFINE) {
           const double* __restrict__ A = pc.aff + slot * 24;
           if constexpr (N % 2 == 0) {
 #pragma unroll
@@ -239,7 +239,7 @@ __device__ __forceinline__ void relax_lcp(const double (&g)[N], const double* __
 // ---------------------------------------------------------------------------------------------------------------
 // default / thresholded ground state of one pixel.  nd[] <- occupations (integers when kT == 0).
 // ---------------------------------------------------------------------------------------------------------------
-template <int N, bool THERMAL>
+template <int N, bool THERMAL, bool AFFINE>
 __device__ __forceinline__ void ground_state_box(const double (&g)[N], const double* __restrict__ rec,
                                                  const qd_layout& L, const ProjCache& pc, int lane, bool thresholded,
                                                  double kT, double fx, double fy, double (&nd)[N]) {
@@ -257,7 +257,7 @@ __device__ __forceinline__ void ground_state_box(const double (&g)[N], const dou
   double nc[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) nc[j] = g[j];
-  if (__any_sync(0xffffffffu, neg)) relax_lcp<N>(g, rec + L.o_cdd, pc, lane, fx, fy, nc);
+  if (__any_sync(0xffffffffu, neg)) relax_lcp<N, AFFINE>(g, rec + L.o_cdd, pc, lane, fx, fy, nc);
 
   double f[N], r[N], lin[N];
 #pragma unroll
@@ -607,7 +607,8 @@ __device__ __forceinline__ uint64_t pack_key(const double (&nd)[N], bool integra
 
 // THERMAL = false instantiations carry no Boltzmann-average code at all (the hard-argmin kernels are the hot ones; the
 // launch picks THERMAL = true only when QD_FLAG_THERMAL is set).
-template <int N, int ALG, bool THERMAL>
+// POINTS = true: explicit voltage list (a.points) instead of the affine descriptor -- the single-device entry points.
+template <int N, int ALG, bool THERMAL, bool POINTS>
 __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kernel(const KArgs a) {
   extern __shared__ __align__(128) unsigned char qd_smem[];
   const int lane = threadIdx.x & 31;
@@ -633,7 +634,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
   pc.meta = pc.keys + QD_PC_WAYS;
   pc.lin_s = pc.aug + 8 * 16 + 8;
   pc.aff = pc.lin_s + 8 * 32;
-  pc.gsrc = (a.points == nullptr) ? der : nullptr;
+  pc.gsrc = POINTS ? nullptr : der;
 
   if (lane == 0) mbar_init(bar, 1);
   __syncwarp();
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
     if (row0 >= ny) { __syncwarp(); continue; }
 
     // ---- affine coefficients of the dot potentials and of the sensor potential ----
-    if (a.points == nullptr) {
+    if constexpr (!POINTS) {
       if (lane <= N) {
         const double* arow = (lane < N) ? rec + L.o_a + lane * NV : rec + L.o_sa;
         double s0 = 0.0, sx = 0.0, sy = 0.0;
@@ -729,7 +730,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
         float zf;
         if (!replace) {
           // ---- dot potentials g = cgd . v ----
-          if (a.points == nullptr) {
+          if constexpr (!POINTS) {
             const double fx = (double)ixc, fy = (double)iy;
 #pragma unroll
             for (int j = 0; j < N; ++j) g[j] = fma(fy, d_gy[j], fma(fx, d_gx[j], d_g0[j]));
@@ -754,7 +755,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
 #pragma unroll
             for (int j = 0; j < N; ++j) nd[j] = src[j];
           } else if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N, THERMAL>(g, rec, L, kT, nd);
-          else ground_state_box<N, THERMAL>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, (double)ixc, (double)iy, nd);
+          else ground_state_box<N, THERMAL, !POINTS>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, (double)ixc, (double)iy, nd);
 
           // ---- hysteresis latching along x ----
           if (latch_on) {
