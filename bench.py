@@ -422,6 +422,9 @@ def main():
             "peak_kind": "fp64 FMA micro-benchmark run inside this bench (qd_measure_fp64_peak); "
                          "MEASURED_PEAKS.json has no CUDA-core figure",
             "flop_per_pixel": f_exec, "flop_per_pixel_reference_formulation": f_ref,
+            "binding": "instruction issue across the ALU / FP64 / LSU pipes (ncu, profiles/r01_ncu_summary.md: issue slots "
+                       "52 % busy, ALU 37 %, LSU 23 %, FP64 16 % of their pipes); HBM 1.6 %. The path is a per-pixel 8 x 8 "
+                       "fp64 quadratic form with data-dependent control flow: no tensor-core shape, not HBM bound",
             "pipe_slot_frac": pix_s_kernel * fp64_pipe_ops_factored(N) * 2e-12 / fp64_peak,
             "kernel_ms": k_ms, "fp32_peak": fp32_peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
