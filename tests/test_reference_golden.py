@@ -115,15 +115,24 @@ def test_oracle_matches_reference(name):
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/src/qarray_latched"), reason="reference tree not present")
 def test_reference_regenerates_fixture():
-    """The committed fixture is what the reference produces today (guards against a stale or hand-edited file)."""
+    """The committed fixtures are what the reference produces today (guards against stale or hand-edited files): one of
+    each family is regenerated from /root/reference and compared."""
     import sys
     sys.path.insert(0, os.path.join(HERE, "golden"))
     import make_reference_golden as gen
-    name = "ref_4dot_tunnel_identity_vgm"
-    out = gen.run_reference(gen.case_inputs(**gen.CASES[name]))
-    d = load(name)
-    np.testing.assert_allclose(out["n"], d["n"], rtol=0, atol=1e-12)
-    np.testing.assert_allclose(out["z"], d["z"], rtol=0, atol=1e-12)
+    for name in ("ref_4dot_tunnel_identity_vgm", "ref_6dot_tunnel_linear_capacitance"):
+        out = gen.run_reference(gen.case_inputs(**gen.CASES[name]))
+        d = load(name)
+        np.testing.assert_allclose(out["n"], d["n"], rtol=0, atol=1e-12)
+        np.testing.assert_allclose(out["z"], d["z"], rtol=0, atol=1e-12)
+    out = gen.run_reference_path_a(**gen.CASES_A["ref_a_4dot_32x32"])
+    d = load_a("ref_a_4dot_32x32")
+    assert np.array_equal(out["n"], d["n"])
+    np.testing.assert_allclose(out["n_continuous"], d["n_continuous"], rtol=0, atol=1e-12)
+    out = gen.run_reference_virtualisation()
+    d = dict(np.load(os.path.join(HERE, "golden", "ref_virtualisation.npz")))
+    for k in ("kalman_k3_means", "direct_k2_variances", "vgm_electrons", "vgm_target_holes"):
+        np.testing.assert_allclose(out[k], d[k], rtol=0, atol=1e-12)
     import qarray                                             # the product's packages are back after the shim context
     assert "rl-agent-for-qubit-array-tuning_b200" in qarray.__file__
 
