@@ -1,5 +1,7 @@
 """Batched observation stage (first 'next' row): descriptor synthesis on the CPU, percentile
 normalisation and the whole observe() call on the GPU."""
+import os
+
 import numpy as np
 import pytest
 
@@ -149,3 +151,32 @@ def test_agent_views_follow_the_reference_channel_and_transpose_rule():
             assert views[f"barrier_{j}"]["voltage"][e, 0] == obs["obs_barrier_voltages"][e, j]
     # views, not copies, for the single-channel agents
     assert views["barrier_2"]["image"].data_ptr() == obs["image"][:, 2:3].data_ptr()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/qadapt/utils/vary_peak_width.py") and
+                    not os.path.exists("/root/reference/src/qadapt/environment/utils/vary_peak_width.py"),
+                    reason="reference tree not present")
+def test_variable_peak_width_matches_reference_class():
+    """obs_scans(peak_width_alpha=...) against the reference's own VaryPeakWidth (utils/vary_peak_width.py), imported
+    as it is (pure NumPy)."""
+    import glob
+    import importlib.util
+    from qdsim import obs, synth
+    path = glob.glob("/root/reference/src/qadapt/**/vary_peak_width.py", recursive=True)[0]
+    spec = importlib.util.spec_from_file_location("ref_vpw", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    e, n = 3, 4
+    dev = synth.sample_devices(e, n, seed=9)
+    mb = synth.model_batch(dev)
+    rng = np.random.default_rng(2)
+    gate_v = rng.uniform(-40, 40, size=(e, n))
+    alpha = rng.uniform(1e-4, 8e-3, size=e)
+    pw0 = dev["peak_width"]
+    scans = obs.obs_scans(mb, gate_v, 0.0, np.broadcast_to(-np.eye(n + 1), (e, n + 1, n + 1)), np.zeros((e, n + 1)), -1.5,
+                          1.5, 16, peak_width=pw0, peak_width_alpha=alpha)
+    for env in range(e):
+        ref = mod.VaryPeakWidth(pw0[env], alpha[env])
+        for ch in range(n - 1):
+            want = ref.linearly_vary_peak_width(gate_v[env, ch], gate_v[env, ch + 1])
+            assert scans["peak_width"][env * (n - 1) + ch] == want
