@@ -180,3 +180,49 @@ def test_variable_peak_width_matches_reference_class():
         for ch in range(n - 1):
             want = ref.linearly_vary_peak_width(gate_v[env, ch], gate_v[env, ch + 1])
             assert scans["peak_width"][env * (n - 1) + ch] == want
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/qadapt/environment/qarray_base_class.py"),
+                    reason="reference tree not present")
+def test_radial_noise_descriptor_and_oracle_match_the_reference_method(monkeypatch):
+    """S7: QarrayBaseClass._apply_radial_noise (qarray_base_class.py:444-493), compiled from the reference's source text and
+    run with np.random.randn replaced by known normals, against obs_scans' radial descriptor + the oracle's radial_noise --
+    both branches (additive ramp, full replacement)."""
+    import ast
+    import types
+    from oracle import noise
+    from qdsim import obs, synth
+    path = "/root/reference/src/qadapt/environment/qarray_base_class.py"
+    tree = ast.parse(open(path).read(), filename=path)
+    body = [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "_apply_radial_noise"]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    res, e, n = 16, 2, 3
+    dev = synth.sample_devices(e, n, seed=4)
+    mb = synth.model_batch(dev)
+    rng = np.random.default_rng(8)
+    gt = rng.uniform(-5, 5, size=(e, n))
+    gate_v = gt + np.array([[3.0, -25.0, 28.0], [45.0, 2.0, -1.0]])          # env 1, pair 0 lies beyond full_noise_distance
+    radial = dict(zero_radius=np.array([22.0, 25.0]), ramp_distance=np.array([30.0, 33.0]),
+                  full_noise_distance=np.array([35.0, 38.0]), max_amplitude=0.05)
+    window = np.array([1.6, 1.9])
+    scans = obs.obs_scans(mb, gate_v, 0.0, np.broadcast_to(-np.eye(n + 1), (e, n + 1, n + 1)), np.zeros((e, n + 1)),
+                          -window, window, res, gate_ground_truth=gt, radial=radial, seeds=np.arange(e * (n - 1)))
+    normals = rng.standard_normal((res, res))
+    monkeypatch.setattr(np.random, "randn", lambda *shape: normals.reshape(shape))
+    z = rng.uniform(0.2, 1.0, size=(res, res))
+    modes = []
+    for env in range(e):
+        me = types.SimpleNamespace(radial_noise_config={"enabled": True, "max_amplitude": 0.05},
+                                   radial_noise_full_noise_distance=radial["full_noise_distance"][env],
+                                   radial_noise_zero_radius=radial["zero_radius"][env],
+                                   radial_noise_ramp_distance=radial["ramp_distance"][env],
+                                   obs_voltage_min=-window[env], obs_voltage_max=window[env], obs_image_size=res)
+        for ch in range(n - 1):
+            want = ns["_apply_radial_noise"](me, z, gate_v[env, ch], gate_v[env, ch + 1], gt[env, ch], gt[env, ch + 1])
+            rec = scans[env * (n - 1) + ch]
+            got = noise.radial_noise(z, normals, int(rec["rad_mode"]), rec["rad_x0"], rec["rad_dx"], rec["rad_y0"],
+                                     rec["rad_dy"], rec["rad_alpha"], rec["rad_zero_radius"], rec["rad_max_amp"])
+            np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-14)
+            modes.append(int(rec["rad_mode"]))
+    assert set(modes) == {1, 2}
