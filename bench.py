@@ -171,6 +171,55 @@ def cpu_reference_scan_seconds(mb, scans, flags, threads: int) -> float:
     return cport.run_scans(mb, scans, flags, threads=threads)[2]
 
 
+def parity_sample(mb, scans, flags, z, n, pick, res: int, threads: int = 0):
+    """CHECKER leg (the only use of oracle/ here besides the CPU baselines): re-run the scans ``pick`` of the timed batch
+    with the plain-C restatement and compare -- charge maps bit for bit on rows without near-ties, images at 5e-6.
+    ``z`` [pixels] / ``n`` [pixels, N]: this run's outputs (NumPy or CUDA tensors)."""
+    from util import cport_parity
+    pick = np.asarray(pick)
+    pp = res * res
+    if hasattr(z, "is_cuda"):
+        import torch
+        idx = torch.from_numpy(pick).to(z.device)
+        zs = z.view(-1, pp)[idx].cpu().numpy().reshape(-1)
+        ns = n.view(-1, pp, n.shape[-1])[idx].cpu().numpy().reshape(-1, n.shape[-1])
+    else:
+        zs = np.asarray(z).reshape(-1, pp)[pick].reshape(-1)
+        ns = np.asarray(n).reshape(-1, pp, np.asarray(n).shape[-1])[pick].reshape(-1, np.asarray(n).shape[-1])
+    sub = scans[pick].copy()
+    sub["pix_offset"] = np.arange(len(sub), dtype=np.int64) * pp
+    rep = cport_parity(mb, sub, flags, zs, ns, threads=threads or (os.cpu_count() or 1))
+    rep["what"] = ("random scans of the timed batch re-run by the plain-C restatement (oracle/cport): n bit-exact on rows "
+                   "whose best/second-best margin > 1e-9, z abs 5e-6")
+    return rep
+
+
+def source_sha() -> str:
+    """sha256 over the kernel sources: keys the committed ncu figures (profiles/ncu_figures.json) to the code they were
+    captured from, so a stale figure is reported as stale instead of silently reused."""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(PKG, "csrc")
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(csrc, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def ncu_figure(kernel: str):
+    """Per-kernel figures taken from a committed ncu capture (profiles/ncu_figures.json, written by tools/ncu_figures.py
+    from a .ncu-rep): warp instructions and DRAM bytes per pixel, with the source hash they belong to."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_figures.json")) as f:
+            fig = json.load(f).get(kernel)
+    except (OSError, ValueError):
+        return None
+    if fig is not None:
+        fig = dict(fig)
+        fig["stale"] = fig.get("source_sha") != source_sha()
+    return fig
+
+
 def build_workload(n_env: int, n_dot: int, res: int, rank: int, n_sets: int, path: str = "A"):
     from qdsim import synth
     if path == "B":
@@ -206,11 +255,29 @@ def tunnel_cpu_baseline(mb, scans, budget_s: float = 8.0):
                     "OpenMP over pixels"}
 
 
-def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_env: int = 512):
-    """Path B on the same GPU: n_env envs of the n_dot tunnel-coupled array, device-resident, CUDA events; the NumPy
-    restatement (pinned against the reference itself, tests/test_reference_golden.py) timed on a small sample."""
+def issue_roofline(kernel: str, pixels_per_s: float, sm_count: int, sm_mhz: float):
+    """Issue-slot roofline of a kernel with data-dependent control flow (no flop model): warp instructions per pixel from
+    the committed ncu capture of THIS source (profiles/ncu_figures.json, keyed by source hash) against 4 issue slots per SM
+    per clock at the measured SM clock."""
+    fig = ncu_figure(kernel)
+    if not fig or not fig.get("warp_instr_per_pixel"):
+        return {"kernel": kernel, "bound": "issue", "achieved": None, "peak": None, "frac": None,
+                "note": "no ncu figure committed for this kernel (profiles/ncu_figures.json)"}
+    peak = sm_count * 4 * sm_mhz * 1e6
+    ach = pixels_per_s * fig["warp_instr_per_pixel"]
+    return {"kernel": kernel, "bound": "issue", "achieved": ach, "peak": peak, "unit": "warp-instr/s", "frac": ach / peak,
+            "warp_instr_per_pixel": fig["warp_instr_per_pixel"], "source": fig.get("source"),
+            "figure_source_sha": fig.get("source_sha"), "stale": fig["stale"], "traffic": fig.get("dram_bytes_per_pixel"),
+            "ncu_issue_active_pct": fig.get("issue_active_pct")}
+
+
+def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_env: int = 512, steps: int = 5,
+                      warmup: int = 5, sm_mhz: float = 1965.0):
+    """Path B on the same GPU (what env.step runs in barrier mode): device-resident timing (CUDA events, warmed) AND the
+    end-to-end host-buffer call, the issue-slot roofline from the committed ncu figure, and the C restatement of the
+    reference's formulation on the host cores."""
     import torch
-    from qdsim import N_F32
+    from qdsim import N_F32, N_NONE
     dev, mb, sets = build_workload(n_env, n_dot, res, 0, 1, "B")
     eng.set_models(mb)
     scans = sets[0]
@@ -219,30 +286,39 @@ def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_e
     z = torch.empty(pixels, dtype=torch.float32, device="cuda")
     n = torch.empty((pixels, n_dot), dtype=torch.float32, device="cuda")
     eng.scan_upload(scans, st)
-    eng.scan_launch(z, n, N_F32, flags, st)
+    for _ in range(warmup):
+        eng.scan_launch(z, n, N_F32, flags, st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    steps = 2
+    l0 = eng.launch_count
     e0.record(st)
     for _ in range(steps):
         eng.scan_launch(z, n, N_F32, flags, st)
     e1.record(st)
     torch.cuda.synchronize()
+    launches = eng.launch_count - l0
     ms = e0.elapsed_time(e1) / steps
+    z_host = torch.empty(pixels, dtype=torch.float32).pin_memory().numpy()
+    pin = torch.empty(scans.nbytes, dtype=torch.uint8).pin_memory()
+    pin.numpy()[:] = scans.view(np.uint8)
+    sp = pin.numpy().view(scans.dtype)
+    for _ in range(2):
+        eng.scan_open_host(sp, n_type=N_NONE, flags=flags, z_out=z_host)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        eng.scan_open_host(sp, n_type=N_NONE, flags=flags, z_out=z_host)
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / steps
+    props = torch.cuda.get_device_properties(0)
     blk = {"workload": f"{n_dot}-dot tunnel-coupled array (TunnelCoupledChargeSensed, 32-state basis, barrier voltages), "
                        f"{n_env} envs, {n_dot - 1} scans/env of {res}x{res}, latching + noise",
            "kernels": f"qd_tunnel_gs_kernel<{n_dot}> + qd_scan_kernel<{n_dot},tunnel>",
            "value": pixels / (ms * 1e-3), "unit": "pixels/s", "env_steps_per_s": n_env / (ms * 1e-3),
-           "ms_per_step": ms, "steps": steps, "cpu_baseline": None}
-    # no flop model for this path (data-dependent control flow); what bounds it is instruction issue: warp instructions
-    # per pixel from the committed ncu capture (profiles/r01_ncu_summary.md) against 4 issue slots per SM per clock
-    instr = {8: 13280.0, 4: 9500.0}.get(n_dot)
-    if instr:
-        props = torch.cuda.get_device_properties(0)
-        peak = props.multi_processor_count * 4 * 1.965e9
-        blk["issue_roofline"] = {"warp_instr_per_pixel": instr, "source": "ncu smsp__inst_executed.sum / pixels (profiles/)",
-                                 "achieved": blk["value"] * instr, "peak": peak, "unit": "warp-instr/s",
-                                 "frac": blk["value"] * instr / peak}
+           "ms_per_step": ms, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
+           "e2e": {"value": pixels / (e2e_ms * 1e-3), "unit": "pixels/s", "env_steps_per_s": n_env / (e2e_ms * 1e-3),
+                   "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(scans.nbytes), "d2h_bytes_per_step": int(pixels * 4)},
+           "roofline": issue_roofline(f"qd_tunnel_gs_kernel<{n_dot}>", pixels / (ms * 1e-3), props.multi_processor_count,
+                                      sm_mhz),
+           "cpu_baseline": None}
     if with_cpu:
         blk["cpu_baseline"] = tunnel_cpu_baseline(mb, scans)
     return blk
@@ -260,6 +336,9 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=0, help="scans in the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-path-b", action="store_true", help="skip the secondary tunnel-coupled measurement")
+    ap.add_argument("--no-compact", action="store_true", help="skip the compact-format (uint8 / half) end-to-end runs")
+    ap.add_argument("--parity-scans", type=int, default=2048,
+                    help="scans of the timed batch re-run by the C restatement and compared (0 = skip)")
     ap.add_argument("--path", default="A", choices=["A", "B"],
                     help="A: constant-interaction ChargeSensedDotArray path (headline); B: tunnel-coupled path of "
                          "env.step in barrier mode (secondary; use e.g. --n-dot 4 --n-env 1024)")
@@ -280,7 +359,9 @@ def main():
         workload = (f"{N}-dot tunnel-coupled array (32-state basis, barrier voltages), {args.n_env} envs/GPU, {N - 1} "
                     f"scans/env of {res}x{res}, latching + white/telegraph/radial noise")
     config = {"workload": workload, "n_dot": N, "n_env_per_gpu": args.n_env, "res": res,
-              "scans_per_env": N - 1, "l2": "inputs+outputs per step >> L2 (outputs alone 12 B/pixel)"}
+              "scans_per_env": N - 1, "l2": "inputs+outputs per step >> L2 (outputs alone 12 B/pixel)",
+              "value_inputs": "model records and scan descriptors resident in HBM when the timed region starts; "
+                              "e2e includes the per-step descriptor H2D and the image D2H"}
 
     # ---------------------------------------------------------------- reference arm: CPU only, rank 0 only
     if args.impl == "reference":
@@ -373,15 +454,23 @@ def main():
     total_ms = max_over_ranks(ev[0].elapsed_time(ev[-1]))
     ms_per_step = total_ms / args.steps
     value = world * pixels / (ms_per_step * 1e-3)
-    checksum = float(n_dev[:: max(1, pixels // 4096)].double().sum().item())
+
+    # ---- parity on the timed batch itself (outside every timed region; rank 0) ----
+    parity = None
+    if rank == 0 and args.path == "A" and args.parity_scans > 0:
+        rng = np.random.default_rng(2026)
+        pick = np.sort(rng.choice(n_scan, size=min(args.parity_scans, n_scan), replace=False))
+        parity = parity_sample(mb, sets[0], flags, z_dev, n_dev, pick, res)
 
     # ---- (2) end to end through the host-buffer path ----
     pinned_scans = [torch.empty(s.nbytes, dtype=torch.uint8).pin_memory() for s in sets]
     for t, s in zip(pinned_scans, sets):
         t.numpy()[:] = s.view(np.uint8)
     z_host = torch.empty(pixels, dtype=torch.float32).pin_memory()
-
     z_host_np = z_host.numpy()
+    obs_u8 = torch.empty(pixels, dtype=torch.uint8).pin_memory().numpy()
+    obs_f16 = torch.empty(pixels, dtype=torch.float16).pin_memory().numpy()
+    from qdsim import Z_F16, Z_U8
 
     def e2e_step(k):
         # the reference-facing host-buffer call: descriptors H2D from pinned memory, compute, sensor images D2H into
@@ -389,20 +478,49 @@ def main():
         s = pinned_scans[k % n_sets].numpy().view(sets[0].dtype)
         eng.scan_open_host(s, n_type=N_NONE, flags=flags, z_out=z_host_np)
 
-    for k in range(2):
-        e2e_step(k)
-    barrier()
-    # the call is synchronous (returns with the images in host memory), so the host clock brackets exactly the device
-    # work + copies; barrier + synchronize on both sides, max over ranks
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        e2e_step(k)
-    torch.cuda.synchronize()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    clocks = sampler.stop() if rank == 0 else None          # sampled across both timed regions
-    barrier()
-    e2e_ms = max_over_ranks(wall_ms) / args.steps
+    def e2e_obs_u8(k):
+        # compact observation: percentile-normalised per env on the device, uint8, one quarter of the bytes
+        s = pinned_scans[k % n_sets].numpy().view(sets[0].dtype)
+        eng.scan_obs_host(s, z_type=Z_U8, flags=flags, normalise=True, out=obs_u8)
+
+    def e2e_obs_f16(k):
+        s = pinned_scans[k % n_sets].numpy().view(sets[0].dtype)
+        eng.scan_obs_host(s, z_type=Z_F16, flags=flags, normalise=False, out=obs_f16)
+
+    def time_e2e(fn):
+        for k in range(2):
+            fn(k)
+        barrier()
+        # the call is synchronous (returns with the images in host memory), so the host clock brackets exactly the device
+        # work + copies; barrier + synchronize on both sides, max over ranks
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            fn(k)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        barrier()
+        per_rank = [wall / args.steps]
+        if world > 1:
+            t = torch.tensor([wall / args.steps], dtype=torch.float64, device="cuda")
+            allr = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allr, t)
+            per_rank = [float(x.item()) for x in allr]
+        return max(per_rank), per_rank
+
+    e2e_ms, e2e_ranks = time_e2e(e2e_step)
+    clocks = sampler.stop() if rank == 0 else None          # sampled across the device-resident and the fp32 e2e regions
     e2e_value = world * pixels / (e2e_ms * 1e-3)
+    compact = {}
+    if args.path == "A" and not args.no_compact:
+        for name, fn, bpp, what in (("obs_u8", e2e_obs_u8, 1, "per-env percentile-normalised observation, uint8 (what the policy is fed, env.py:471-509)"),
+                                    ("raw_f16", e2e_obs_f16, 2, "raw sensor signal, IEEE half")):
+            ms_c, ranks_c = time_e2e(fn)
+            compact[name] = {"value": world * pixels / (ms_c * 1e-3), "unit": "pixels/s", "ms_per_step": ms_c,
+                             "per_rank_ms": ranks_c, "d2h_bytes_per_step": int(pixels * bpp),
+                             "h2d_bytes_per_step": int(sets[0].nbytes), "format": what}
+    # the host-buffer path returns the very images of the device-resident launch (same descriptors -> same pixels)
+    e2e_step(0)
+    e2e_same = bool(torch.equal(z_host.cuda(), z_dev)) if args.path == "A" else None
 
     # ---- (3) roofline of the dominant kernel (rank 0) ----
     out = None
@@ -416,30 +534,41 @@ def main():
         achieved = pix_s_kernel * f_exec * 1e-12
         bytes_per_pixel = 4 + N
         hbm_achieved = pix_s_kernel * bytes_per_pixel * 1e-9
+        kname = f"qd_scan_kernel<{N},default>"
+        fig = ncu_figure(kname)
+        sm_mhz = float((clocks or {}).get("sm_mhz") or 1965.0)
+        sm_count = torch.cuda.get_device_properties(local_rank).multi_processor_count
         roofline = {
-            "bound": "fp64_pipe", "kernel": f"qd_scan_kernel<{N},default>",
+            "bound": "fp64_pipe", "kernel": kname,
             "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            # two numerators, both against the measured FP64 FMA peak: the factored search the kernel has to execute, and
+            # SURVEY 8(d)'s count of the REFERENCE formulation (every candidate a full quadratic form).  The second exceeds
+            # 1: the kernel does not do that work -- exact dominance pruning + Gray-code walk reach the same argmin.
+            "frac_factored": achieved / fp64_peak,
+            "frac_survey_formulation": pix_s_kernel * f_ref * 1e-12 / fp64_peak,
             "peak_kind": "fp64 FMA micro-benchmark run inside this bench (qd_measure_fp64_peak); "
                          "MEASURED_PEAKS.json has no CUDA-core figure",
             "flop_per_pixel": f_exec, "flop_per_pixel_reference_formulation": f_ref,
-            "binding": "instruction issue across the ALU / FP64 / LSU pipes (ncu, profiles/r01_ncu_summary.md: issue slots "
-                       "52 % busy, ALU 37 %, LSU 23 %, FP64 16 % of their pipes); HBM 1.6 %. The path is a per-pixel 8 x 8 "
-                       "fp64 quadratic form with data-dependent control flow: no tensor-core shape, not HBM bound",
+            "binding": "instruction issue (see `issue`): a per-pixel 8 x 8 fp64 quadratic form with data-dependent control "
+                       "flow -- no tensor-core shape, HBM at a few percent",
+            "issue": issue_roofline(kname, pix_s_kernel, sm_count, sm_mhz),
             "pipe_slot_frac": pix_s_kernel * fp64_pipe_ops_factored(N) * 2e-12 / fp64_peak,
             "kernel_ms": k_ms, "fp32_peak": fp32_peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
-            # (profiles/r01_ncu_summary.md: 687 MB per launch of 58.7 Mpixel = 11.7 B/pixel), scaled to this launch
-            "traffic": 11.7 * pixels if (N == 8 and args.path == "A") else None,
-            "traffic_source": "ncu --set full capture at 2048 envs (profiles/), scaled per pixel",
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture of THIS source
+            # (profiles/ncu_figures.json; `traffic_stale` says when the kernel sources changed since)
+            "traffic": (fig["dram_bytes_per_pixel"] * pixels) if fig and fig.get("dram_bytes_per_pixel") else None,
+            "traffic_stale": fig["stale"] if fig else None,
+            "traffic_source": (fig or {}).get("source"),
             "hbm": {"achieved": hbm_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": hbm_achieved / peaks["hbm_gbs"], "peak_kind": peak_kind,
                     "algorithmic_bytes_per_pixel": bytes_per_pixel},
         }
         cpu = None
         if args.path == "B":
-            roofline.update({"kernel": f"qd_tunnel_gs_kernel<{N}> + qd_scan_kernel<{N},tunnel>", "achieved": None,
-                             "frac": None, "flop_per_pixel": None, "pipe_slot_frac": None,
-                             "note": "secondary path: no flop model yet; see profiles/"})
+            roofline = issue_roofline(f"qd_tunnel_gs_kernel<{N}>", pix_s_kernel, sm_count, sm_mhz)
+            roofline["kernel_ms"] = k_ms
+            if world == 1 and not args.no_cpu_baseline:
+                cpu = tunnel_cpu_baseline(mb, sets[0])
         if world == 1 and not args.no_cpu_baseline and args.path == "A":
             cores = os.cpu_count() or 1
             pps, cpix, cdt, kind = cpu_reference_pixels_per_s(mb, sets[0], flags, args.cpu_scans, cores)
@@ -453,13 +582,19 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pixels/s", "env_steps_per_s": e2e_value / pix_per_env,
-                    "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / args.steps,
-                    "h2d_bytes_per_step": int(sets[0].nbytes), "d2h_bytes_per_step": int(pixels * 4)},
-            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "checksum": checksum,
+                    "ms_per_step": e2e_ms, "per_rank_ms": e2e_ranks, "format": "fp32 sensor images (the parity format)",
+                    "h2d_bytes_per_step": int(sets[0].nbytes), "d2h_bytes_per_step": int(pixels * 4),
+                    "matches_device_resident_launch": e2e_same},
+            "e2e_compact": compact or None,
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity,
+            "parity_note": "latching / noise semantics are the restatement's (qarray wheel absent: parity unpinned there, "
+                           "DESIGN.md section 2); the check above pins the CUDA path to that restatement on the benched batch",
+            "source_sha": source_sha(),
         }
     # ---- (4) secondary: the tunnel-coupled path that QADAPT's env.step executes in barrier mode (Path B) ----
     if rank == 0 and world == 1 and args.path == "A" and not args.no_path_b:
-        out["env_step_tunnel_path"] = tunnel_path_block(eng, N, res, flags, not args.no_cpu_baseline)
+        out["env_step_tunnel_path"] = tunnel_path_block(eng, N, res, flags, not args.no_cpu_baseline,
+                                                        sm_mhz=float((clocks or {}).get("sm_mhz") or 1965.0))
     # the one collective of the design, OFF the step path: per-env episode statistics to every rank (NCCL all-gather)
     if world > 1:
         from qdsim import parallel

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 2
+#define QD_ABI_VERSION 3
 #define QD_MAX_DOTS 8   /* BASELINE.json configs go to 8 dots                                  */
 #define QD_MAX_VOLT 16  /* n_gate + n_barrier = (N+1) + (N-1)                                  */
 
@@ -42,6 +42,15 @@ enum qd_algorithm { QD_ALG_DEFAULT = 0, QD_ALG_THRESHOLDED = 1, QD_ALG_BRUTE_FOR
 
 /* Output element type of the charge map. */
 enum qd_ntype { QD_N_NONE = 0, QD_N_U8 = 1, QD_N_F32 = 2, QD_N_F64 = 3 };
+
+/* Element type of a compact observation image (qd_scan_obs_host / qd_normalise_obs_typed): fp32, IEEE half, or uint8
+ * = rint(255 * x) of an image normalised to [0, 1].  fp32 stays the parity format; the compact types exist because the
+ * host-buffer path is bound by the device-to-host copy of the images, not by the kernels. */
+enum qd_ztype { QD_Z_F32 = 0, QD_Z_F16 = 1, QD_Z_U8 = 2 };
+
+/* bits of qd_status() */
+#define QD_STATUS_OCC_OVERFLOW 0x1u  /* a scan window reaches occupations >= 254 carriers per dot: uint8 charge maps  */
+                                     /* and the packed latching keys would saturate (results of that launch invalid) */
 
 /* flags of qd_scan_open / qd_points_open */
 #define QD_FLAG_LATCH            0x01u  /* apply the envs' LatchingModel (S5)                              */
@@ -164,6 +173,28 @@ int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const 
  * Asynchronous on `stream`. */
 int qd_normalise_obs(qd_ctx* ctx, const float* z, float* out, int64_t per_env, int n_env, double q_low_pct,
                      double q_high_pct, double* stats, void* stream);
+
+/* qd_normalise_obs with a typed output (enum qd_ztype): out holds n_env * per_env elements of z_type; QD_Z_U8 stores
+ * rint(255 * x).  z, out, stats are DEVICE pointers. */
+int qd_normalise_obs_typed(qd_ctx* ctx, const float* z, void* out, int z_type, int64_t per_env, int n_env,
+                           double q_low_pct, double q_high_pct, double* stats, void* stream);
+
+/* The observation of one batched env.step, delivered to HOST memory in a compact element type: simulate the scans
+ * (as qd_scan_open_host), optionally percentile-normalise per env on the device (QuantumDeviceEnv._normalise_obs,
+ * env.py:471-509 -- what the policy is fed), convert to z_type and copy back; chunks of envs are pipelined so that the
+ * copy of one chunk overlaps the kernels of the next.
+ *   scans          env-major: scans_per_env consecutive descriptors per env, all of one size, pix_offset = i * nx * ny
+ *   out_host       [n_scan * ny * nx] elements of z_type (pinned memory for full copy speed)
+ *   normalise      0: raw sensor signal (QD_Z_F32 / QD_Z_F16 only); 1: percentile-normalised to [0, 1]
+ *   stats_host     [n_scan / scans_per_env, 2] doubles (p_low, p_high per env) or NULL
+ */
+int qd_scan_obs_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, int scans_per_env, void* out_host, int z_type,
+                     int normalise, double q_low_pct, double q_high_pct, double* stats_host, unsigned flags);
+
+/* Sticky status bits (QD_STATUS_*) raised by the kernels of this context; `clear` != 0 resets them.  The *_host entry
+ * points check it themselves and return QD_ERR_INVALID; callers of the asynchronous entry points call this after
+ * synchronising their stream. */
+int qd_status(qd_ctx* ctx, int clear);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 int64_t qd_launch_count(const qd_ctx* ctx);

@@ -38,30 +38,34 @@ def _load():
             build()
         lib = C.CDLL(_LIB)
         vp = C.c_void_p
-        lib.qd_cport_scans.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, vp, C.c_int]
+        lib.qd_cport_scans.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_uint, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int]
         lib.qd_cport_scans.restype = C.c_int
         _lib = lib
     return _lib
 
 
-def run_scans(mb, scans, flags: int, threads: int = 0, want_n: bool = True):
+def run_scans(mb, scans, flags: int, threads: int = 0, want_n: bool = True, want_margin: bool = False):
     """``mb``: a ModelBatch-like object (cdd_inv_gs, cdd_gs, cdd_inv_full, cgd_full, params, algorithm);
-    ``scans``: qd_scan records.  Returns (z float32 [pixels], n float64 [pixels, N] or None, seconds)."""
+    ``scans``: qd_scan records.  Returns (z float32 [pixels], n float64 [pixels, N] or None, seconds) -- with
+    ``want_margin`` a fourth item: the best / second-best candidate energy gap of every pixel, float64 [pixels]."""
     lib = _load()
     scans = np.ascontiguousarray(scans)
     pixels = int((scans["pix_offset"] + scans["nx"].astype(np.int64) * scans["ny"]).max())
     n_dot = mb.cdd_inv_gs.shape[-1]
     z = np.empty(pixels, dtype=np.float32)
     n = np.empty((pixels, n_dot), dtype=np.float64) if want_n else None
+    margin = np.full(pixels, np.inf) if want_margin else None
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (mb.cdd_inv_gs, mb.cdd_gs, mb.cdd_inv_full, mb.cgd_full)]
     params = np.ascontiguousarray(mb.params)
     t0 = time.perf_counter()
     rc = lib.qd_cport_scans(len(scans), scans.ctypes.data, n_dot, mb.cgd_full.shape[-1], ALG[mb.algorithm], flags,
                             *[a.ctypes.data for a in arrs], params.ctypes.data, z.ctypes.data,
-                            None if n is None else n.ctypes.data, threads)
+                            None if n is None else n.ctypes.data, None if margin is None else margin.ctypes.data, threads)
     dt = time.perf_counter() - t0
     if rc != 0:
         raise RuntimeError(f"qd_cport_scans failed: {rc}")
+    if want_margin:
+        return z, n, dt, margin
     return z, n, dt
 
 

@@ -88,8 +88,10 @@ static double energy(int n, const double* conf, const double* g, const double* c
 
 /* ground state of one pixel; returns occupations in nd */
 static void ground_state(int n, int alg, const double* g, const double* cinv, const double* cdd, double thr, int maxc,
-                         double kT, double* nd) {
-  double conf[MAXN], best_conf[MAXN], best = INFINITY;
+                         double kT, double* nd, double* margin) {
+  /* *margin <- second-lowest minus lowest candidate energy (oracle/path_a.py::_select): the tie detector of the
+   * parity checks (an exact tie has no defined winner across two summation orders) */
+  double conf[MAXN], best_conf[MAXN], best = INFINITY, second = INFINITY;
   if (alg == QD_ALG_BRUTE_FORCE) {
     long total = 1;
     for (int i = 0; i < n; ++i) total *= (maxc + 1);
@@ -99,11 +101,12 @@ static void ground_state(int n, int alg, const double* g, const double* cinv, co
         long t = c;
         for (int i = n - 1; i >= 0; --i) { conf[i] = (double)(t % (maxc + 1)); t /= (maxc + 1); }
         double e = energy(n, conf, g, cinv);
-        if (pass == 0) { if (e < best) { best = e; memcpy(best_conf, conf, sizeof(double) * n); } }
+        if (pass == 0) { if (e < best) { second = best; best = e; memcpy(best_conf, conf, sizeof(double) * n); } else if (e < second) second = e; }
         else { double wgt = exp(-(e - best) / kT); z += wgt; for (int i = 0; i < n; ++i) acc[i] += wgt * conf[i]; }
       }
     }
     for (int i = 0; i < n; ++i) nd[i] = kT > 0 ? acc[i] / z : best_conf[i];
+    if (margin) *margin = second - best;
     return;
   }
   double nc[MAXN], fl[MAXN];
@@ -128,16 +131,17 @@ static void ground_state(int n, int alg, const double* g, const double* cinv, co
       }
       if (!ok) continue;
       double e = energy(n, conf, g, cinv);
-      if (pass == 0) { if (e < best) { best = e; memcpy(best_conf, conf, sizeof(double) * n); } }
+      if (pass == 0) { if (e < best) { second = best; best = e; memcpy(best_conf, conf, sizeof(double) * n); } else if (e < second) second = e; }
       else { double wgt = exp(-(e - best) / kT); z += wgt; for (int i = 0; i < n; ++i) acc[i] += wgt * conf[i]; }
     }
   }
   for (int i = 0; i < n; ++i) nd[i] = kT > 0 ? acc[i] / z : best_conf[i];
+  if (margin) *margin = second - best;
 }
 
 static void scan_rows(const qd_scan* s, int n, int nv, int alg, unsigned flags, const double* cinv, const double* cdd,
                       const double* cinv_full, const double* cgd_full, const qd_env_params* p, int row0, int row1,
-                      float* z_out, double* n_out) {
+                      float* z_out, double* n_out, double* margin_out) {
   const int d = n + 1, nx = s->nx;
   const double kT = (flags & QD_FLAG_THERMAL) ? p->kT : 0.0;
   const int latch = (flags & QD_FLAG_LATCH) && p->latching;
@@ -159,7 +163,9 @@ static void scan_rows(const qd_scan* s, int n, int nv, int alg, unsigned flags, 
       double v[QD_MAX_VOLT], g[MAXN], nd[MAXN];
       for (int k = 0; k < nv; ++k) v[k] = (s->v0[k] + ix * s->dx[k]) + iy * s->dy[k];
       for (int i = 0; i < n; ++i) { double a = 0; for (int k = 0; k < nv; ++k) a += cgd_full[i * nv + k] * v[k]; g[i] = a; }
-      ground_state(n, alg, g, cinv, cdd, p->threshold, p->max_charge_carriers, kT, nd);
+      double mg = INFINITY;
+      ground_state(n, alg, g, cinv, cdd, p->threshold, p->max_charge_carriers, kT, nd, margin_out ? &mg : NULL);
+      if (margin_out) margin_out[s->pix_offset + (int64_t)pix] = mg;
       if (latch) {
         double key[MAXN];
         for (int i = 0; i < n; ++i) key[i] = (flags & QD_FLAG_LATCH_EXACT) ? nd[i] : floor(nd[i] + 0.5);
@@ -217,7 +223,7 @@ static void scan_rows(const qd_scan* s, int n, int nv, int alg, unsigned flags, 
 /* Simulate n_scan scans on `threads` OpenMP threads.  Arrays are per env, same layout as qd_set_models. */
 int qd_cport_scans(int n_scan, const qd_scan* scans, int n_dot, int n_volt, int algorithm, unsigned flags,
                    const double* cdd_inv_gs, const double* cdd_gs, const double* cdd_inv_full, const double* cgd_full,
-                   const qd_env_params* params, float* z_out, double* n_out, int threads) {
+                   const qd_env_params* params, float* z_out, double* n_out, double* margin_out, int threads) {
   const int n = n_dot, d = n_dot + 1, nv = n_volt;
   if (n < 1 || n > MAXN || nv > QD_MAX_VOLT) return -1;
 #ifdef _OPENMP
@@ -230,7 +236,7 @@ int qd_cport_scans(int n_scan, const qd_scan* scans, int n_dot, int n_volt, int 
       const qd_scan* s = scans + i;
       const int e = s->env_id;
       scan_rows(s, n, nv, algorithm, flags, cdd_inv_gs + (size_t)e * n * n, cdd_gs + (size_t)e * n * n,
-                cdd_inv_full + (size_t)e * d * d, cgd_full + (size_t)e * d * nv, params + e, 0, s->ny, z_out, n_out);
+                cdd_inv_full + (size_t)e * d * d, cgd_full + (size_t)e * d * nv, params + e, 0, s->ny, z_out, n_out, margin_out);
     }
   } else {
     for (int i = 0; i < n_scan; ++i) {
@@ -239,7 +245,7 @@ int qd_cport_scans(int n_scan, const qd_scan* scans, int n_dot, int n_volt, int 
 #pragma omp parallel for schedule(dynamic, 1)
       for (int iy = 0; iy < s->ny; ++iy)
         scan_rows(s, n, nv, algorithm, flags, cdd_inv_gs + (size_t)e * n * n, cdd_gs + (size_t)e * n * n,
-                  cdd_inv_full + (size_t)e * d * d, cgd_full + (size_t)e * d * nv, params + e, iy, iy + 1, z_out, n_out);
+                  cdd_inv_full + (size_t)e * d * d, cgd_full + (size_t)e * d * nv, params + e, iy, iy + 1, z_out, n_out, margin_out);
     }
   }
   return 0;

@@ -41,6 +41,21 @@ struct qd_ctx {
   size_t pts_cap = 0;
   double* d_nbar = nullptr;       // tunnel path: <n> of every pixel between the two launches
   size_t nbar_cap = 0;
+  void* d_obs = nullptr;          // qd_scan_obs_host: compact (typed) observation images before the copy-back
+  size_t obs_cap = 0;
+  double* d_stats = nullptr;      // qd_scan_obs_host: per-env (p_low, p_high)
+  size_t stats_cap = 0;
+  unsigned* h_status = nullptr;   // sticky QD_STATUS_* word: mapped pinned host memory, kernels write it on errors only
+  unsigned* d_status = nullptr;   // its device alias
+  unsigned char* h_small = nullptr;   // mapped pinned output buffer of the small-call fast path (kernel writes it directly)
+  unsigned char* d_small = nullptr;   // its device alias
+  size_t small_cap = 0;
+  cudaEvent_t last_launch = nullptr;  // recorded after every launch: the context's scratch (d_scans, d_nbar) is free
+  cudaStream_t last_stream = nullptr; //   for a launch on ANOTHER stream only once this has fired
+  bool have_last = false;
+  bool staged_pending = false;    // an asynchronous H2D out of h_scans may still be in flight
+  const void* configured[64] = {nullptr};   // kernels whose shared-memory attributes are already set
+  int n_configured = 0;
   cudaEvent_t staged = nullptr;   // h_scans may be rewritten once this has fired
   cudaStream_t s_compute = nullptr, s_copy = nullptr;   // qd_scan_open_host: launches / result copies, overlapped
   cudaEvent_t chunk_done[16] = {nullptr};
@@ -142,8 +157,43 @@ int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) 
   if (n_type != QD_N_NONE && !n_out) return fail(ctx, QD_ERR_INVALID, "n_out is NULL but n_type != QD_N_NONE");
   if ((flags & QD_FLAG_THERMAL) && n_type == QD_N_U8)
     return fail(ctx, QD_ERR_INVALID, "QD_FLAG_THERMAL yields non-integer occupations: use QD_N_F32/F64 or QD_N_NONE");
-  if ((flags & QD_FLAG_THERMAL) && (flags & QD_FLAG_LATCH) && (flags & QD_FLAG_LATCH_EXACT))
-    return fail(ctx, QD_ERR_UNSUPPORTED, "exact-compare latching of thermal (non-integer) occupations is not supported");
+  // QD_FLAG_LATCH_EXACT: with integer occupations (hard argmin) the raw and the rounded compare coincide, so the flag
+  // is accepted and changes nothing; on non-integer occupations (thermal average, tunnel path) the kernel only has the
+  // rounded compare -- refuse instead of silently answering a different question.
+  if ((flags & QD_FLAG_LATCH) && (flags & QD_FLAG_LATCH_EXACT) &&
+      ((flags & QD_FLAG_THERMAL) || ctx->L.algorithm == QD_ALG_TUNNEL))
+    return fail(ctx, QD_ERR_UNSUPPORTED,
+                "QD_FLAG_LATCH_EXACT: exact-compare latching of non-integer occupations (thermal / tunnel path) is not supported");
+  if (ctx->L.algorithm == QD_ALG_TUNNEL && n_type == QD_N_U8)
+    return fail(ctx, QD_ERR_INVALID, "the tunnel path yields non-integer occupations <n>: use QD_N_F32/F64 or QD_N_NONE");
+  return QD_OK;
+}
+
+// shared-memory attributes of a kernel: set once per context (two driver calls saved per launch)
+int configure_kernel(qd_ctx* ctx, const void* fn, size_t smem) {
+  for (int i = 0; i < ctx->n_configured; ++i)
+    if (ctx->configured[i] == fn) return QD_OK;
+  // every slot size of a kernel is fixed by the model layout, which can change: ask for the architectural maximum once
+  (void)smem;
+  QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  // every warp stages its own record: ask for the largest shared-memory carveout so that registers, not shared
+  // memory, bound the resident warps
+  QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  if (ctx->n_configured < 64) ctx->configured[ctx->n_configured++] = fn;
+  return QD_OK;
+}
+
+// The context's scratch buffers (d_scans, d_nbar) are shared by all launches.  A launch on stream B that follows one on
+// stream A must not re-stage them before A's kernels are done with them: every launch records `last_launch`, and work
+// enqueued on a different stream waits for it first (same stream: already ordered, no call made).
+int order_after_last_launch(qd_ctx* ctx, cudaStream_t stream) {
+  if (ctx->have_last && ctx->last_stream != stream) QD_CUDA(ctx, cudaStreamWaitEvent(stream, ctx->last_launch, 0));
+  return QD_OK;
+}
+int mark_launch(qd_ctx* ctx, cudaStream_t stream) {
+  QD_CUDA(ctx, cudaEventRecord(ctx->last_launch, stream));
+  ctx->last_stream = stream;
+  ctx->have_last = true;
   return QD_OK;
 }
 
@@ -163,6 +213,7 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
     qd::KArgs g;
     g.L = ctx->L; g.records = ctx->d_records; g.scans = d_scans; g.points = d_points; g.z_out = nullptr;
     g.n_out = nullptr; g.nbar = ctx->d_nbar; g.n_scan = n_scan; g.n_type = QD_N_NONE; g.flags = flags;
+    g.status = ctx->d_status;
     g.slot_bytes = qd::qd_tunnel_slot_bytes(ctx->L);
     const long long max_pix = ctx->up_max_pix;
     const long long want_items = (long long)ctx->sm_count * 12 * 4;
@@ -176,9 +227,8 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
     long long ggrid = (items + gw - 1) / gw;
     if (ggrid > 0x7fffffffLL) ggrid = 0x7fffffffLL;
     const size_t gsmem = (size_t)g.slot_bytes * gw;
-    if (gsmem > 48 * 1024)
-      QD_CUDA(ctx, cudaFuncSetAttribute((const void*)gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-    QD_CUDA(ctx, cudaFuncSetAttribute((const void*)gs, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    rc = configure_kernel(ctx, (const void*)gs, gsmem);
+    if (rc) return rc;
     gs<<<(unsigned)ggrid, gw * 32, gsmem, stream>>>(g);
     QD_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
@@ -193,6 +243,7 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   a.n_scan = n_scan;
   a.n_type = n_type;
   a.flags = flags;
+  a.status = ctx->d_status;
   a.slot_bytes = qd::qd_slot_bytes(ctx->L);
   // item = block of rows of one scan handled by one warp.  Large batches: one scan per warp (staging amortised over
   // the whole scan).  Small batches: split rows so that every SM gets work.  A flat (carry-rows) pass is sequential
@@ -211,31 +262,40 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   long long grid = (total_items + wpc - 1) / wpc;
   if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
   const size_t smem = (size_t)a.slot_bytes * wpc;
-  if (smem > 48 * 1024)
-    QD_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  // every warp stages its own record: ask for the largest shared-memory carveout so that registers, not shared
-  // memory, bound the resident warps
-  QD_CUDA(ctx, cudaFuncSetAttribute((const void*)fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  {
+    const int rc2 = configure_kernel(ctx, (const void*)fn, smem);
+    if (rc2) return rc2;
+  }
   fn<<<(unsigned)grid, wpc * 32, smem, stream>>>(a);
   QD_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
-  return QD_OK;
+  return mark_launch(ctx, stream);
 }
 
-int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stream, int* max_ny) {
+int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stream, int* max_ny,
+                bool caller_syncs = false) {
   if (n_scan <= 0) return fail(ctx, QD_ERR_INVALID, "n_scan must be positive");
   if (!scans) return fail(ctx, QD_ERR_INVALID, "scans is NULL");
   const size_t bytes = (size_t)n_scan * sizeof(qd_scan);
   int rc = grow(ctx, &ctx->d_scans, &ctx->scans_cap, bytes);
   if (rc) return rc;
+  rc = order_after_last_launch(ctx, stream);     // an earlier launch on another stream may still read d_scans
+  if (rc) return rc;
   // Descriptors already in pinned host memory (e.g. a torch pin_memory() buffer) are copied straight from there and
-  // must stay untouched until the copy has run; pageable ones go through the context's pinned staging buffer.
-  cudaPointerAttributes attr;
-  const bool pinned = cudaPointerGetAttributes(&attr, scans) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  if (!pinned) cudaGetLastError();
+  // must stay untouched until the copy has run; pageable ones go through the context's pinned staging buffer.  A few
+  // descriptors are always staged (the memcpy is cheaper than asking the driver what kind of pointer it is).
+  bool pinned = false;
+  if (bytes > 64 * 1024) {
+    cudaPointerAttributes attr;
+    pinned = cudaPointerGetAttributes(&attr, scans) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+  }
   const qd_scan* src = scans;
   if (!pinned) {
-    QD_CUDA(ctx, cudaEventSynchronize(ctx->staged));   // the previous H2D out of the staging buffer has finished
+    if (ctx->staged_pending) {
+      QD_CUDA(ctx, cudaEventSynchronize(ctx->staged));   // the previous H2D out of the staging buffer has finished
+      ctx->staged_pending = false;
+    }
     if (ctx->h_scans_cap < bytes) {
       if (ctx->h_scans) cudaFreeHost(ctx->h_scans);
       ctx->h_scans = nullptr;
@@ -249,7 +309,10 @@ int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stre
   }
   // the copy is issued first and runs while the host validates the descriptors (nothing is launched on a failure)
   QD_CUDA(ctx, cudaMemcpyAsync(ctx->d_scans, src, bytes, cudaMemcpyHostToDevice, stream));
-  QD_CUDA(ctx, cudaEventRecord(ctx->staged, stream));
+  if (!pinned && !caller_syncs) {
+    QD_CUDA(ctx, cudaEventRecord(ctx->staged, stream));
+    ctx->staged_pending = true;
+  }
   ctx->up_n_scan = 0;
   int mny = 0;
   long long ext = 0, mpix = 0;
@@ -270,6 +333,89 @@ int stage_scans(qd_ctx* ctx, int n_scan, const qd_scan* scans, cudaStream_t stre
   ctx->up_pixels = ext;
   ctx->up_max_pix = mpix;
   return QD_OK;
+}
+
+// sticky status word -> error of a synchronous entry point
+int check_status(qd_ctx* ctx) {
+  const unsigned st = *reinterpret_cast<volatile unsigned*>(ctx->h_status);
+  if (!st) return QD_OK;
+  *ctx->h_status = 0u;
+  if (st & QD_STATUS_OCC_OVERFLOW)
+    return fail(ctx, QD_ERR_INVALID,
+                "a scan window reaches 252 or more carriers on a dot: outside the 0..255 range of the uint8 charge map "
+                "and of the packed latching keys");
+  return fail(ctx, QD_ERR_INVALID, "kernel status 0x%x", st);
+}
+
+// Pipeline plan of the *_host entry points: the scans are cut into chunks (multiples of `align` scans) whose output pixel
+// ranges [lo, hi) are disjoint and increasing; chunk c+1 computes on one stream while chunk c's images travel back over
+// PCIe on another.  Chunk sizes: equal, except that the last three halve (1, ..., 1, 1/2, 1/4, 1/8): the copy of the LAST
+// chunk is the only one that cannot hide behind compute, so it is kept small as long as it still fills the chip.
+struct ChunkPlan {
+  int n_chunk = 1;
+  std::vector<int> cut;
+  std::vector<long long> lo, hi;
+  bool tiled = true;       // the scans tile [0, pixels) without gaps
+};
+
+ChunkPlan plan_chunks(const qd_ctx* ctx, int n_scan, const qd_scan* scans, int align) {
+  ChunkPlan P;
+  const long long pixels = ctx->up_pixels;
+  int n_chunk = n_scan / 2048;          // >= 2048 scans per chunk keeps every launch a full-chip wave or more
+  int chunk_cap = 16;                   // measured (host-buffer pipeline): 16 chunks 43.6 ms, 12: 44.3, 8: 45.4
+  if (const char* e = getenv("QDSIM_PIPE_CHUNKS")) chunk_cap = atoi(e) > 0 ? atoi(e) : chunk_cap;
+  if (chunk_cap > 16) chunk_cap = 16;   // chunk_done[16]
+  if (n_chunk > chunk_cap) n_chunk = chunk_cap;
+  if (n_chunk < 1) n_chunk = 1;
+  if (align < 1) align = 1;
+  long long sum = 0;
+  for (int i = 0; i < n_scan; ++i) sum += (long long)scans[i].nx * scans[i].ny;
+  P.tiled = sum == pixels;
+  P.cut.assign(n_chunk + 1, 0);
+  {
+    std::vector<double> w(n_chunk, 1.0);
+    if (n_chunk >= 6) { w[n_chunk - 3] = 0.5; w[n_chunk - 2] = 0.25; w[n_chunk - 1] = 0.125; }
+    double tot = 0.0;
+    for (double x : w) tot += x;
+    if (n_chunk >= 6 && (double)n_scan * w[n_chunk - 1] / tot < 2048.0) { std::fill(w.begin(), w.end(), 1.0); tot = n_chunk; }
+    double acc = 0.0;
+    for (int c = 0; c < n_chunk; ++c) {
+      acc += w[c];
+      int at = (int)((double)n_scan * acc / tot);
+      at -= at % align;
+      P.cut[c + 1] = std::max(at, P.cut[c]);
+    }
+    P.cut[n_chunk] = n_scan;
+  }
+  P.lo.assign(n_chunk, 0);
+  P.hi.assign(n_chunk, 0);
+  bool ok = true;
+  for (int c = 0; c < n_chunk && ok; ++c) {
+    long long a = -1, b = 0;
+    for (int i = P.cut[c]; i < P.cut[c + 1]; ++i) {
+      const long long p0 = scans[i].pix_offset, p1 = p0 + (long long)scans[i].nx * scans[i].ny;
+      if (a < 0 || p0 < a) a = p0;
+      if (p1 > b) b = p1;
+    }
+    if (a < 0) ok = false;                                   // empty chunk
+    P.lo[c] = a; P.hi[c] = b;
+    if (c > 0 && P.lo[c] < P.hi[c - 1]) ok = false;          // output ranges interleave: no pipeline
+  }
+  if (!ok || n_chunk == 1) {
+    P.n_chunk = 1;
+    P.cut.assign({0, n_scan});
+    P.lo.assign({0});
+    P.hi.assign({pixels});
+  } else {
+    P.n_chunk = n_chunk;
+  }
+  return P;
+}
+
+int pipe_rows_cap() {
+  int rows_cap = 16;
+  if (const char* e = getenv("QDSIM_PIPE_ROWS")) rows_cap = atoi(e) > 0 ? atoi(e) : rows_cap;
+  return rows_cap;
 }
 
 }  // namespace
@@ -322,6 +468,12 @@ int qd_create(int device, qd_ctx** out) {
   e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->staged, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->last_launch, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&ctx->h_status, 64, cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *ctx->h_status = 0u;
+    e = cudaHostGetDevicePointer((void**)&ctx->d_status, ctx->h_status, 0);
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking);
   for (int i = 0; i < 16 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&ctx->chunk_done[i], cudaEventDisableTiming);
@@ -345,6 +497,11 @@ void qd_destroy(qd_ctx* ctx) {
   if (ctx->d_n) cudaFree(ctx->d_n);
   if (ctx->d_pts) cudaFree(ctx->d_pts);
   if (ctx->d_nbar) cudaFree(ctx->d_nbar);
+  if (ctx->d_obs) cudaFree(ctx->d_obs);
+  if (ctx->d_stats) cudaFree(ctx->d_stats);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  if (ctx->h_small) cudaFreeHost(ctx->h_small);
+  if (ctx->last_launch) cudaEventDestroy(ctx->last_launch);
   if (ctx->staged) cudaEventDestroy(ctx->staged);
   for (int i = 0; i < 16; ++i) if (ctx->chunk_done[i]) cudaEventDestroy(ctx->chunk_done[i]);
   if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
@@ -493,71 +650,165 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   if (rc) return rc;
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
   int max_ny = 0;
-  rc = stage_scans(ctx, n_scan, scans, ctx->s_compute, &max_ny);
+  rc = stage_scans(ctx, n_scan, scans, ctx->s_compute, &max_ny, true);
   if (rc) return rc;
   const long long pixels = ctx->up_pixels;
   const int N = ctx->L.n_dot;
   const size_t esz = n_elem_size(n_type);
+  const size_t zbytes = z_out_host ? (size_t)pixels * sizeof(float) : 0, nbytes = (size_t)pixels * N * esz;
+
+  // ---- small calls (a single do2d_open): the kernel writes its outputs straight into mapped pinned host memory, so the
+  // call is one descriptor copy, one launch (two on the tunnel path) and one synchronisation -- no device-to-host copies
+  if (zbytes + nbytes <= (1u << 20) && n_scan <= 64) {
+    const size_t zoff = (zbytes + 255) & ~(size_t)255;
+    const size_t need = zoff + nbytes + 256;
+    if (ctx->small_cap < need) {
+      if (ctx->h_small) cudaFreeHost(ctx->h_small);
+      ctx->h_small = ctx->d_small = nullptr;
+      ctx->small_cap = 0;
+      QD_CUDA(ctx, cudaHostAlloc((void**)&ctx->h_small, (1u << 20) + 4096, cudaHostAllocMapped));
+      QD_CUDA(ctx, cudaHostGetDevicePointer((void**)&ctx->d_small, ctx->h_small, 0));
+      ctx->small_cap = (1u << 20) + 4096;
+    }
+    long long sum = 0;
+    for (int i = 0; i < n_scan; ++i) sum += (long long)scans[i].nx * scans[i].ny;
+    if (sum != pixels) memset(ctx->h_small, 0, need);          // gaps between scans read as zeros
+    rc = launch(ctx, n_scan, ctx->d_scans, max_ny, nullptr, z_out_host ? (float*)ctx->d_small : nullptr,
+                ctx->d_small + zoff, n_type, flags, ctx->s_compute);
+    if (rc) return rc;
+    QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    ctx->staged_pending = false;
+    if (z_out_host) memcpy(z_out_host, ctx->h_small, zbytes);
+    if (nbytes) memcpy(n_out_host, ctx->h_small + zoff, nbytes);
+    return check_status(ctx);
+  }
+
   rc = grow(ctx, &ctx->d_z, &ctx->z_cap, (size_t)pixels * sizeof(float));
   if (rc) return rc;
   if (esz) {
     rc = grow(ctx, (unsigned char**)&ctx->d_n, &ctx->n_cap, (size_t)pixels * N * esz);
     if (rc) return rc;
   }
-  // Large batches run as a pipeline: the scans are cut into chunks whose output pixel ranges are disjoint and
-  // increasing; chunk c+1 computes on one stream while chunk c's images travel back over PCIe on another.
-  int n_chunk = n_scan / 2048;          // >= 2048 scans per chunk keeps every launch a full-chip wave or more
-  int chunk_cap = 16, rows_cap = 16;   // measured (host-buffer pipeline): 16 chunks 43.6 ms, 12: 44.3, 8: 45.4
-  if (const char* e = getenv("QDSIM_PIPE_CHUNKS")) chunk_cap = atoi(e) > 0 ? atoi(e) : chunk_cap;
-  if (const char* e = getenv("QDSIM_PIPE_ROWS")) rows_cap = atoi(e) > 0 ? atoi(e) : rows_cap;
-  if (chunk_cap > 16) chunk_cap = 16;   // chunk_done[16]
-  if (n_chunk > chunk_cap) n_chunk = chunk_cap;
-  if (n_chunk < 1) n_chunk = 1;
-  std::vector<int> cut(n_chunk + 1);
-  std::vector<long long> lo(n_chunk), hi(n_chunk);
-  // Chunk sizes: equal, except that the last three halve (1, ..., 1, 1/2, 1/4, 1/8).  The copy of the LAST chunk is the
-  // only one that cannot hide behind compute, so it is kept small (about 2 % of the images at 8 chunks) as long as it
-  // still fills the chip.
-  {
-    std::vector<double> w(n_chunk, 1.0);
-    if (n_chunk >= 6) { w[n_chunk - 3] = 0.5; w[n_chunk - 2] = 0.25; w[n_chunk - 1] = 0.125; }
-    double tot = 0.0;
-    for (double x : w) tot += x;
-    if (n_chunk >= 6 && (double)n_scan * w[n_chunk - 1] / tot < 2048.0) { std::fill(w.begin(), w.end(), 1.0); tot = n_chunk; }
-    double acc = 0.0;
-    cut[0] = 0;
-    for (int c = 0; c < n_chunk; ++c) { acc += w[c]; cut[c + 1] = (int)((double)n_scan * acc / tot); }
-    cut[n_chunk] = n_scan;
+  const ChunkPlan P = plan_chunks(ctx, n_scan, scans, 1);
+  if (!P.tiled) {
+    // the copies below move whole pixel ranges: what lies between the scans must not be stale device memory
+    if (z_out_host) QD_CUDA(ctx, cudaMemsetAsync(ctx->d_z, 0, (size_t)pixels * sizeof(float), ctx->s_compute));
+    if (esz) QD_CUDA(ctx, cudaMemsetAsync(ctx->d_n, 0, (size_t)pixels * N * esz, ctx->s_compute));
   }
-  for (int c = 0; c < n_chunk; ++c) {
-    long long a = -1, b = 0;
-    for (int i = cut[c]; i < cut[c + 1]; ++i) {
-      const long long p0 = scans[i].pix_offset, p1 = p0 + (long long)scans[i].nx * scans[i].ny;
-      if (a < 0 || p0 < a) a = p0;
-      if (p1 > b) b = p1;
-    }
-    lo[c] = a; hi[c] = b;
-    if (c > 0 && lo[c] < hi[c - 1]) { n_chunk = 1; cut[1] = n_scan; lo[0] = 0; hi[0] = pixels; break; }
-  }
-  if (n_chunk == 1) { cut[0] = 0; cut[1] = n_scan; lo[0] = 0; hi[0] = pixels; }
+  const int rows_cap = pipe_rows_cap();
   const long long all_pixels = ctx->up_pixels;
-  for (int c = 0; c < n_chunk; ++c) {
+  for (int c = 0; c < P.n_chunk; ++c) {
     ctx->up_pixels = all_pixels;      // the tunnel scratch is addressed with the scans' own pixel offsets
-    rc = launch(ctx, cut[c + 1] - cut[c], ctx->d_scans + cut[c], max_ny, nullptr, ctx->d_z, ctx->d_n, n_type, flags,
-                ctx->s_compute, n_chunk > 1 ? rows_cap : 0);
+    rc = launch(ctx, P.cut[c + 1] - P.cut[c], ctx->d_scans + P.cut[c], max_ny, nullptr, ctx->d_z, ctx->d_n, n_type, flags,
+                ctx->s_compute, P.n_chunk > 1 ? rows_cap : 0);
     if (rc) return rc;
     QD_CUDA(ctx, cudaEventRecord(ctx->chunk_done[c], ctx->s_compute));
     QD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->chunk_done[c], 0));
+    const long long lo = P.lo[c], hi = P.hi[c];
     if (z_out_host)
-      QD_CUDA(ctx, cudaMemcpyAsync(z_out_host + lo[c], ctx->d_z + lo[c], (size_t)(hi[c] - lo[c]) * sizeof(float),
+      QD_CUDA(ctx, cudaMemcpyAsync(z_out_host + lo, ctx->d_z + lo, (size_t)(hi - lo) * sizeof(float),
                                    cudaMemcpyDeviceToHost, ctx->s_copy));
     if (esz)
-      QD_CUDA(ctx, cudaMemcpyAsync((char*)n_out_host + (size_t)lo[c] * N * esz, (char*)ctx->d_n + (size_t)lo[c] * N * esz,
-                                   (size_t)(hi[c] - lo[c]) * N * esz, cudaMemcpyDeviceToHost, ctx->s_copy));
+      QD_CUDA(ctx, cudaMemcpyAsync((char*)n_out_host + (size_t)lo * N * esz, (char*)ctx->d_n + (size_t)lo * N * esz,
+                                   (size_t)(hi - lo) * N * esz, cudaMemcpyDeviceToHost, ctx->s_copy));
   }
   QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
   QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+  ctx->staged_pending = false;
+  return check_status(ctx);
+}
+
+namespace {
+size_t z_elem_size(int z_type) { return z_type == QD_Z_F32 ? 4 : z_type == QD_Z_F16 ? 2 : z_type == QD_Z_U8 ? 1 : 0; }
+
+int normalise_typed(qd_ctx* ctx, const float* z, void* out, int z_type, int64_t per_env, int n_env, double q_low_pct,
+                    double q_high_pct, double* stats, cudaStream_t stream) {
+  const double ql = q_low_pct / 100.0, qh = q_high_pct / 100.0;
+  switch (z_type) {
+    case QD_Z_F32: qd::qd_normalise_kernel<float><<<n_env, 512, 0, stream>>>(z, (float*)out, per_env, n_env, ql, qh, stats); break;
+    case QD_Z_F16: qd::qd_normalise_kernel<__half><<<n_env, 512, 0, stream>>>(z, (__half*)out, per_env, n_env, ql, qh, stats); break;
+    case QD_Z_U8: qd::qd_normalise_kernel<unsigned char><<<n_env, 512, 0, stream>>>(z, (unsigned char*)out, per_env, n_env, ql, qh, stats); break;
+    default: return fail(ctx, QD_ERR_INVALID, "bad z_type %d", z_type);
+  }
+  QD_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
   return QD_OK;
+}
+}  // namespace
+
+int qd_scan_obs_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, int scans_per_env, void* out_host, int z_type,
+                     int normalise, double q_low_pct, double q_high_pct, double* stats_host, unsigned flags) {
+  int rc = validate_launch(ctx, QD_N_NONE, flags, nullptr);
+  if (rc) return rc;
+  if (!out_host) return fail(ctx, QD_ERR_INVALID, "out_host is NULL");
+  const size_t zsz = z_elem_size(z_type);
+  if (!zsz) return fail(ctx, QD_ERR_INVALID, "bad z_type %d", z_type);
+  if (!normalise && z_type == QD_Z_U8) return fail(ctx, QD_ERR_INVALID, "QD_Z_U8 needs a normalised image (normalise = 1)");
+  if (scans_per_env <= 0 || n_scan <= 0 || n_scan % scans_per_env != 0)
+    return fail(ctx, QD_ERR_INVALID, "n_scan (%d) must be a positive multiple of scans_per_env (%d)", n_scan, scans_per_env);
+  if (normalise && !(q_low_pct >= 0.0 && q_low_pct <= q_high_pct && q_high_pct <= 100.0))
+    return fail(ctx, QD_ERR_INVALID, "percentiles must satisfy 0 <= low <= high <= 100");
+  if (!scans) return fail(ctx, QD_ERR_INVALID, "scans is NULL");
+  const long long per_scan = (long long)scans[0].nx * scans[0].ny;
+  for (int i = 0; i < n_scan; ++i)
+    if (scans[i].nx != scans[0].nx || scans[i].ny != scans[0].ny || scans[i].pix_offset != (long long)i * per_scan)
+      return fail(ctx, QD_ERR_INVALID, "scan %d: the observation path needs equal-size scans with pix_offset = i * nx * ny", i);
+  QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int max_ny = 0;
+  rc = stage_scans(ctx, n_scan, scans, ctx->s_compute, &max_ny, true);
+  if (rc) return rc;
+  const long long pixels = ctx->up_pixels;
+  const int n_env_b = n_scan / scans_per_env;
+  const long long per_env = per_scan * scans_per_env;
+  rc = grow(ctx, &ctx->d_z, &ctx->z_cap, (size_t)pixels * sizeof(float));
+  if (rc) return rc;
+  const bool direct = !normalise && z_type == QD_Z_F32;        // raw fp32: copied straight out of d_z
+  if (!direct) {
+    rc = grow(ctx, (unsigned char**)&ctx->d_obs, &ctx->obs_cap, (size_t)pixels * zsz);
+    if (rc) return rc;
+  }
+  if (normalise) {
+    rc = grow(ctx, &ctx->d_stats, &ctx->stats_cap, (size_t)n_env_b * 2 * sizeof(double));
+    if (rc) return rc;
+  }
+  const ChunkPlan P = plan_chunks(ctx, n_scan, scans, scans_per_env);
+  const int rows_cap = pipe_rows_cap();
+  const long long all_pixels = ctx->up_pixels;
+  for (int c = 0; c < P.n_chunk; ++c) {
+    ctx->up_pixels = all_pixels;
+    rc = launch(ctx, P.cut[c + 1] - P.cut[c], ctx->d_scans + P.cut[c], max_ny, nullptr, ctx->d_z, nullptr, QD_N_NONE, flags,
+                ctx->s_compute, P.n_chunk > 1 ? rows_cap : 0);
+    if (rc) return rc;
+    const long long lo = P.lo[c], hi = P.hi[c];
+    const int env0 = P.cut[c] / scans_per_env, envs = (P.cut[c + 1] - P.cut[c]) / scans_per_env;
+    const char* src = (const char*)ctx->d_z + (size_t)lo * 4;
+    if (normalise) {
+      rc = normalise_typed(ctx, ctx->d_z + lo, (char*)ctx->d_obs + (size_t)lo * zsz, z_type, per_env, envs, q_low_pct,
+                           q_high_pct, ctx->d_stats + 2 * (size_t)env0, ctx->s_compute);
+      if (rc) return rc;
+      src = (const char*)ctx->d_obs + (size_t)lo * zsz;
+    } else if (z_type == QD_Z_F16) {
+      long long blocks = (hi - lo + 2047) / 2048;
+      if (blocks > 8 * (long long)ctx->sm_count) blocks = 8 * (long long)ctx->sm_count;
+      qd::qd_to_half_kernel<<<(unsigned)blocks, 256, 0, ctx->s_compute>>>(ctx->d_z + lo, (__half*)ctx->d_obs + lo, hi - lo);
+      QD_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 1;
+      src = (const char*)ctx->d_obs + (size_t)lo * zsz;
+    }
+    QD_CUDA(ctx, cudaEventRecord(ctx->chunk_done[c], ctx->s_compute));
+    QD_CUDA(ctx, cudaStreamWaitEvent(ctx->s_copy, ctx->chunk_done[c], 0));
+    QD_CUDA(ctx, cudaMemcpyAsync((char*)out_host + (size_t)lo * zsz, src, (size_t)(hi - lo) * zsz, cudaMemcpyDeviceToHost,
+                                 ctx->s_copy));
+  }
+  if (normalise && stats_host) {
+    QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    QD_CUDA(ctx, cudaMemcpyAsync(stats_host, ctx->d_stats, (size_t)n_env_b * 2 * sizeof(double), cudaMemcpyDeviceToHost,
+                                 ctx->s_copy));
+  }
+  QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_copy));
+  QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+  ctx->staged_pending = false;
+  return check_status(ctx);
 }
 
 int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const double* v, float* z_out_host,
@@ -572,7 +823,7 @@ int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const 
   s.ny = ny;
   s.pix_offset = 0;
   int max_ny = 0;
-  rc = stage_scans(ctx, 1, &s, nullptr, &max_ny);
+  rc = stage_scans(ctx, 1, &s, nullptr, &max_ny, true);
   if (rc) return rc;
   const long long pixels = (long long)nx * ny;
   const int N = ctx->L.n_dot, NV = ctx->L.n_volt;
@@ -592,22 +843,31 @@ int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const 
     QD_CUDA(ctx, cudaMemcpyAsync(z_out_host, ctx->d_z, (size_t)pixels * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
   if (nbytes) QD_CUDA(ctx, cudaMemcpyAsync(n_out_host, ctx->d_n, nbytes, cudaMemcpyDeviceToHost, nullptr));
   QD_CUDA(ctx, cudaStreamSynchronize(nullptr));
-  return QD_OK;
+  ctx->staged_pending = false;
+  return check_status(ctx);
 }
 
-int qd_normalise_obs(qd_ctx* ctx, const float* z, float* out, int64_t per_env, int n_env, double q_low_pct,
-                     double q_high_pct, double* stats, void* stream) {
+int qd_normalise_obs_typed(qd_ctx* ctx, const float* z, void* out, int z_type, int64_t per_env, int n_env,
+                           double q_low_pct, double q_high_pct, double* stats, void* stream) {
   if (!ctx) return fail(nullptr, QD_ERR_INVALID, "ctx is NULL");
   if (!z || !out) return fail(ctx, QD_ERR_INVALID, "NULL image pointer");
   if (per_env <= 0 || n_env <= 0) return fail(ctx, QD_ERR_INVALID, "per_env and n_env must be positive");
   if (!(q_low_pct >= 0.0 && q_low_pct <= q_high_pct && q_high_pct <= 100.0))
     return fail(ctx, QD_ERR_INVALID, "percentiles must satisfy 0 <= low <= high <= 100");
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
-  qd::qd_normalise_kernel<<<n_env, 512, 0, (cudaStream_t)stream>>>(z, out, per_env, n_env, q_low_pct / 100.0,
-                                                                     q_high_pct / 100.0, stats);
-  QD_CUDA(ctx, cudaGetLastError());
-  ctx->launches += 1;
-  return QD_OK;
+  return normalise_typed(ctx, z, out, z_type, per_env, n_env, q_low_pct, q_high_pct, stats, (cudaStream_t)stream);
+}
+
+int qd_normalise_obs(qd_ctx* ctx, const float* z, float* out, int64_t per_env, int n_env, double q_low_pct,
+                     double q_high_pct, double* stats, void* stream) {
+  return qd_normalise_obs_typed(ctx, z, out, QD_Z_F32, per_env, n_env, q_low_pct, q_high_pct, stats, stream);
+}
+
+int qd_status(qd_ctx* ctx, int clear) {
+  if (!ctx || !ctx->h_status) return 0;
+  const unsigned st = *reinterpret_cast<volatile unsigned*>(ctx->h_status);
+  if (clear) *ctx->h_status = 0u;
+  return (int)st;
 }
 
 int qd_measure_fp64_peak(qd_ctx* ctx, int iters, double* tflops) { return measure_peak<double>(ctx, iters, tflops); }

@@ -7,6 +7,7 @@
 // histograms, four ranks tracked at once), then one more pass normalises in fp64 and writes fp32.  HBM-bound:
 // 5 reads + 1 write of 4 B per pixel.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,7 +27,13 @@ __device__ __forceinline__ double np_lerp(double a, double b, double t) {
   return (t >= 0.5) ? b - d * (1.0 - t) : a + d * t;
 }
 
-__global__ void __launch_bounds__(512) qd_normalise_kernel(const float* __restrict__ z, float* __restrict__ out,
+// typed store of a normalised value in [0, 1]: fp32, IEEE half, or uint8 = rint(255 v)
+__device__ __forceinline__ void store_norm(float* p, double v) { *p = (float)v; }
+__device__ __forceinline__ void store_norm(__half* p, double v) { *p = __float2half_rn((float)v); }
+__device__ __forceinline__ void store_norm(unsigned char* p, double v) { *p = (unsigned char)__double2int_rn(255.0 * v); }
+
+template <typename OUT>
+__global__ void __launch_bounds__(512) qd_normalise_kernel(const float* __restrict__ z, OUT* __restrict__ out,
                                                            long long per_env, int n_env, double q_lo, double q_hi,
                                                            double* __restrict__ stats) {
   __shared__ unsigned hist[4][256];
@@ -50,13 +57,23 @@ __global__ void __launch_bounds__(512) qd_normalise_kernel(const float* __restri
     __syncthreads();
     const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
     const uint32_t p0 = prefix[0], p1 = prefix[1], p2 = prefix[2], p3 = prefix[3];
+    // ranks that still share their prefix share one histogram (all four in the first pass, usually the two of each end
+    // afterwards): count once, copy after the pass -- a quarter / half of the shared-memory atomics
+    const bool d1 = p1 != p0, d2 = p2 != p0 && p2 != p1, d3 = p3 != p0 && p3 != p1 && p3 != p2;
     for (long long i = threadIdx.x; i < per_env; i += blockDim.x) {
       const uint32_t k = f32_key(src[i]);
       const uint32_t b = (k >> shift) & 0xffu, top = k & hi_mask;
       if (top == p0) atomicAdd(&hist[0][b], 1u);
-      if (top == p1) atomicAdd(&hist[1][b], 1u);
-      if (top == p2) atomicAdd(&hist[2][b], 1u);
-      if (top == p3) atomicAdd(&hist[3][b], 1u);
+      if (d1 && top == p1) atomicAdd(&hist[1][b], 1u);
+      if (d2 && top == p2) atomicAdd(&hist[2][b], 1u);
+      if (d3 && top == p3) atomicAdd(&hist[3][b], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      const int b = threadIdx.x;
+      if (!d1) hist[1][b] = hist[0][b];
+      if (!d2) hist[2][b] = (p2 == p0) ? hist[0][b] : hist[1][b];
+      if (!d3) hist[3][b] = (p3 == p0) ? hist[0][b] : (p3 == p1) ? hist[1][b] : hist[2][b];
     }
     __syncthreads();
     if (threadIdx.x < 4) {
@@ -80,12 +97,20 @@ __global__ void __launch_bounds__(512) qd_normalise_kernel(const float* __restri
   if (stats && threadIdx.x == 0) { stats[2 * env] = p_low; stats[2 * env + 1] = p_high; }
   const bool ok = p_high > p_low;
   const double span = p_high - p_low;
-  float* __restrict__ dst = out + (size_t)env * per_env;
+  OUT* __restrict__ dst = out + (size_t)env * per_env;
   for (long long i = threadIdx.x; i < per_env; i += blockDim.x) {
     double v = ok ? ((double)src[i] - p_low) / span : 0.0;
     v = fmin(fmax(v, 0.0), 1.0);
-    dst[i] = (float)v;
+    store_norm(dst + i, v);
   }
 }
 
+}  // namespace qd
+
+namespace qd {
+// raw fp32 -> half conversion of a sensor image (qd_scan_obs_host with normalise = 0, QD_Z_F16)
+__global__ void __launch_bounds__(256) qd_to_half_kernel(const float* __restrict__ z, __half* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(z[i]);
+}
 }  // namespace qd

@@ -17,6 +17,10 @@ ALGORITHMS = {"default": ALG_DEFAULT, "thresholded": ALG_THRESHOLDED, "brute_for
 # enum qd_ntype
 N_NONE, N_U8, N_F32, N_F64 = 0, 1, 2, 3
 N_DTYPES = {N_U8: np.uint8, N_F32: np.float32, N_F64: np.float64}
+# enum qd_ztype (compact observation images)
+Z_F32, Z_F16, Z_U8 = 0, 1, 2
+Z_DTYPES = {Z_F32: np.float32, Z_F16: np.float16, Z_U8: np.uint8}
+STATUS_OCC_OVERFLOW = 0x1
 # flags
 FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, FLAG_THERMAL = 0x01, 0x02, 0x04, 0x08
 FLAG_CARRY_ROWS, FLAG_LATCH_EXACT, FLAG_WHITE_ON_OUTPUT = 0x10, 0x20, 0x40
@@ -59,8 +63,10 @@ def lib_path() -> str:
 
 
 EXPORTS = ("qd_abi_version", "qd_create", "qd_destroy", "qd_last_error", "qd_set_models", "qd_scan_open",
-           "qd_scan_upload", "qd_scan_launch", "qd_scan_open_host", "qd_normalise_obs", "qd_points_open_host", "qd_launch_count", "qd_measure_fp64_peak",
+           "qd_scan_upload", "qd_scan_launch", "qd_scan_open_host", "qd_normalise_obs", "qd_normalise_obs_typed",
+           "qd_scan_obs_host", "qd_status", "qd_points_open_host", "qd_launch_count", "qd_measure_fp64_peak",
            "qd_measure_fp32_peak")
+ABI_VERSION = 3
 
 _lib = None
 
@@ -97,13 +103,19 @@ def load() -> C.CDLL:
     lib.qd_points_open_host.restype = C.c_int
     lib.qd_normalise_obs.argtypes = [vp, vp, vp, C.c_int64, C.c_int, C.c_double, C.c_double, vp, vp]
     lib.qd_normalise_obs.restype = C.c_int
+    lib.qd_normalise_obs_typed.argtypes = [vp, vp, vp, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_double, vp, vp]
+    lib.qd_normalise_obs_typed.restype = C.c_int
+    lib.qd_scan_obs_host.argtypes = [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, C.c_double, C.c_double, vp, C.c_uint]
+    lib.qd_scan_obs_host.restype = C.c_int
+    lib.qd_status.argtypes = [vp, C.c_int]
+    lib.qd_status.restype = C.c_int
     lib.qd_launch_count.argtypes = [vp]
     lib.qd_launch_count.restype = C.c_int64
     lib.qd_measure_fp64_peak.argtypes = [vp, C.c_int, dp]
     lib.qd_measure_fp64_peak.restype = C.c_int
     lib.qd_measure_fp32_peak.argtypes = [vp, C.c_int, dp]
     lib.qd_measure_fp32_peak.restype = C.c_int
-    if lib.qd_abi_version() != 2:
-        raise OSError(f"{path}: ABI version {lib.qd_abi_version()} != 2")
+    if lib.qd_abi_version() != ABI_VERSION:
+        raise OSError(f"{path}: ABI version {lib.qd_abi_version()} != {ABI_VERSION}")
     _lib = lib
     return lib

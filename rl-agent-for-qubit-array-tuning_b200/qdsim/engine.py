@@ -13,7 +13,7 @@ import numpy as np
 from . import _lib, maxwell
 from ._lib import (ALGORITHMS, FLAG_CARRY_ROWS, FLAG_LATCH, FLAG_LATCH_EXACT, FLAG_NOISE, FLAG_RADIAL,  # noqa: F401
                    FLAG_THERMAL, FLAG_WHITE_ON_OUTPUT, N_DTYPES, N_F32, N_F64, N_NONE, N_U8, PARAMS_DTYPE,
-                   QD_MAX_DOTS, QD_MAX_VOLT, SCAN_DTYPE, QdError)
+                   QD_MAX_DOTS, QD_MAX_VOLT, SCAN_DTYPE, Z_DTYPES, Z_F16, Z_F32, Z_U8, QdError)
 
 K_B = 8.617333262145e-5  # eV/K (src/qarray_latched/DotArrays/_helper_functions.py:213-214)
 
@@ -201,8 +201,30 @@ class Engine:
         if n_type != N_NONE:
             n = n_out if n_out is not None else np.empty((pixels, self.models.n_dot), dtype=N_DTYPES[n_type])
         assert z is None or (z.dtype == np.float32 and z.size >= pixels and z.flags.c_contiguous)
+        # the library copies pixels * N elements of n_type into n: a short, mistyped or strided buffer would be overrun
+        assert n is None or (n.dtype == N_DTYPES[n_type] and n.size >= pixels * self.models.n_dot and n.flags.c_contiguous), \
+            "n_out must be a C-contiguous array of the n_type's dtype with at least pixels * n_dot elements"
         self._check(self._lib.qd_scan_open_host(self._ctx, len(scans), _ptr(scans), _ptr(z), _ptr(n), n_type, flags))
         return z, n
+
+    def scan_obs_host(self, scans: np.ndarray, z_type: int = Z_U8, flags: int = 0, normalise: bool = True,
+                      q_low: float = 0.5, q_high: float = 99.5, out: np.ndarray | None = None, want_stats: bool = False,
+                      scans_per_env: int | None = None):
+        """The observation of one batched env.step in HOST memory, compact element type (``Z_F32`` / ``Z_F16`` /
+        ``Z_U8`` = rint(255 x)): scans -> per-env percentile normalisation on the device (env.py:471-509) -> typed
+        copy-back, pipelined over chunks of envs.  ``scans``: env-major, ``scans_per_env`` (default N-1) equal-size
+        descriptors per env.  Returns ``(image [n_scan, ny, nx] of the z_type's dtype, stats [n_env, 2] or None)``."""
+        assert scans.dtype == SCAN_DTYPE and scans.flags.c_contiguous
+        spe = scans_per_env or (self.models.n_dot - 1)
+        ny, nx = int(scans["ny"][0]), int(scans["nx"][0])
+        pixels = len(scans) * ny * nx
+        if out is None:
+            out = np.empty(pixels, dtype=Z_DTYPES[z_type])
+        assert out.dtype == Z_DTYPES[z_type] and out.size >= pixels and out.flags.c_contiguous
+        stats = np.empty((len(scans) // spe, 2), dtype=np.float64) if (want_stats and normalise) else None
+        self._check(self._lib.qd_scan_obs_host(self._ctx, len(scans), _ptr(scans), spe, _ptr(out), z_type,
+                                               1 if normalise else 0, q_low, q_high, _ptr(stats), flags))
+        return out.reshape(-1)[:pixels].reshape(len(scans), ny, nx), stats
 
     def points_open_host(self, scan: np.ndarray, v: np.ndarray, n_type: int = N_F64, flags: int = 0,
                          want_z: bool = True):
@@ -229,7 +251,20 @@ class Engine:
                                                self._stream(stream)))
         return out
 
+    def normalise_obs_typed(self, z, out, z_type: int, per_env: int | None = None, n_env: int | None = None,
+                            q_low: float = 0.5, q_high: float = 99.5, stats=None, stream=None):
+        """``normalise_obs`` into a DEVICE buffer of a compact element type (``Z_F16`` / ``Z_U8``)."""
+        n_env = self.models.n_env if n_env is None else n_env
+        per_env = z.numel() // n_env if per_env is None else per_env
+        self._check(self._lib.qd_normalise_obs_typed(self._ctx, _ptr(z), _ptr(out), z_type, per_env, n_env, q_low, q_high,
+                                                     _ptr(stats), self._stream(stream)))
+        return out
+
     # -- introspection ---------------------------------------------------------------------------------------
+    def status(self, clear: bool = True) -> int:
+        """Sticky ``QD_STATUS_*`` bits raised by this context's kernels (check after synchronising an async launch)."""
+        return int(self._lib.qd_status(self._ctx, 1 if clear else 0))
+
     @property
     def launch_count(self) -> int:
         return int(self._lib.qd_launch_count(self._ctx))

@@ -11,6 +11,11 @@ a batched pseudo-inverse (``qdsim.virtualisation``) after every observation, as 
 
 Observation layout: ``image`` is a CUDA float32 tensor ``[n_env, N-1, res, res]`` (channels first; the reference's
 per-env image is ``(res, res, N-1)``), voltages are NumPy ``[n_env, N]`` / ``[n_env, N-1]`` in [-1, 1].
+
+Lifetime of an observation: the images live in TWO device buffers used alternately, so the observation returned by one
+``reset`` / ``step`` stays valid across exactly one further ``step`` (``obs_t`` and ``obs_{t+1}`` never alias -- what a
+rollout that stores (obs, next_obs) pairs needs; the reference returns a fresh array per step, env.py:290-291).  Keep an
+observation longer than that and you must ``clone()`` it.
 """
 from __future__ import annotations
 
@@ -189,7 +194,12 @@ class BatchedDeviceEnv:
         import torch
         res, E, N = self.cfg.resolution, self.n_env, self.num_dots
         if self.z_dev is None:
-            self.z_dev = torch.empty(E * (N - 1) * res * res, dtype=torch.float32, device=f"cuda:{self.eng.device}")
+            self._z_bufs = [torch.empty(E * (N - 1) * res * res, dtype=torch.float32, device=f"cuda:{self.eng.device}")
+                            for _ in range(2)]
+            self._z_turn = 0
+        # ping-pong: the previous observation (still held by the caller as obs_t) is not overwritten by this one
+        self.z_dev = self._z_bufs[self._z_turn]
+        self._z_turn ^= 1
         flags = FLAG_LATCH | FLAG_NOISE | (FLAG_RADIAL if self.radial else 0)
         image = obs.observe(self.eng, self._scans(), self.z_dev, flags=flags, normalise=True)
         if self.vg_updater is not None:                    # env.py:229 / :292: update right after the observation

@@ -27,7 +27,7 @@ def test_header_declares_the_expected_entry_points():
 def test_library_loads_and_exports_every_declared_symbol():
     from qdsim import _lib
     lib = _lib.load()
-    assert lib.qd_abi_version() == 2
+    assert lib.qd_abi_version() == 3
     for name in _declared_functions():
         assert hasattr(lib, name), f"libqdsim.so does not export {name}"
     assert set(_lib.EXPORTS) == set(_declared_functions())

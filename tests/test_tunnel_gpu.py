@@ -6,12 +6,21 @@ of src/qarray_latched/DotArrays/ground_state.py (oracle/path_b.py).
 import numpy as np
 import pytest
 
-from util import oracle_batch
+from util import assert_z_given_n, explain_latched_mismatches, oracle_batch, sensor_w_max
 
 pytestmark = pytest.mark.gpu
 
 N_ATOL = 1e-6
 GAP_MIN = 1e-5
+
+
+def _assert_z(z, z_ref, n, n_ref, ok, mb, scans, noisy=False):
+    """z at 1e-6 relative given <n> (tests/util.py::assert_z_given_n), per scan (peak width and env vary)."""
+    z_ref = np.asarray(z_ref)
+    z, n, ok = np.asarray(z).reshape(z_ref.shape), np.asarray(n).reshape(np.asarray(n_ref).shape), np.asarray(ok).reshape(z_ref.shape)
+    for i, rec in enumerate(scans):
+        assert_z_given_n(z[i], z_ref[i], n[i], n_ref[i], ok[i], sensor_w_max(mb, int(rec["env_id"])),
+                         float(rec["peak_width"]), noise_atol=5e-6 if noisy else 0.0, what=f"scan {i}:")
 
 
 def _setup(engine, n_dot, n_env, res, seed, **kw):
@@ -36,7 +45,7 @@ def test_tunnel_ground_state_matches_oracle(engine, n_dot, res, n_env):
     assert ok.mean() > 0.9
     assert np.isfinite(n).all() and np.isfinite(z).all()
     np.testing.assert_allclose(n[ok], n_ref[ok], rtol=0, atol=N_ATOL)
-    np.testing.assert_allclose(z[ok], z_ref[ok], rtol=1e-5, atol=1e-7)
+    _assert_z(z, z_ref, n, n_ref, ok, mb, scans)
     assert (np.abs(n_ref - np.rint(n_ref)) > 0.05).any(), "tunnel coupling should smear some transitions"
 
 
@@ -47,12 +56,17 @@ def test_tunnel_with_latching_and_noise(engine):
     scans["rad_zero_radius"], scans["rad_alpha"] = 1.0, 0.02
     z, n = engine.scan_open_host(scans, n_type=N_F64, flags=flags)
     z_ref, n_ref, gap = oracle_batch(mb, scans, flags)
+    _, n_free, _ = oracle_batch(mb, scans, flags & ~FLAG_LATCH)
     z, n = z.reshape(z_ref.shape), n.reshape(n_ref.shape)
-    # a rounded-compare latch decision can flip when <n> sits within 1e-6 of a half-integer: require agreement on
-    # all but a handful of pixels, exact agreement elsewhere
-    bad = np.abs(n - n_ref).max(axis=-1) > N_ATOL
-    assert bad.mean() < 0.01, f"{bad.sum()} of {bad.size} pixels differ"
-    np.testing.assert_allclose(z[~bad], z_ref[~bad], rtol=0, atol=5e-6)
+    # every differing pixel must be EXPLAINED: downstream (same row) of a pixel whose free <n> sits on a half-integer
+    # within the eigen-solver tolerance, or whose spectral gap makes the ground vector ill-conditioned
+    n_dif = n_amb = n_rows = 0
+    for i in range(len(scans)):
+        d, a, r = explain_latched_mismatches(n[i], n_ref[i], n_free[i], gap[i])
+        n_dif, n_amb, n_rows = n_dif + d, n_amb + a, n_rows + r
+    assert n_amb <= 0.05 * n_rows, f"{n_amb} of {n_rows} rows ambiguous: the test has no teeth"
+    same = np.abs(n - n_ref).max(axis=-1) <= N_ATOL
+    _assert_z(z, z_ref, n, n_ref, same, mb, scans, noisy=True)
 
 
 def test_tunnel_points_mode_flat_pass(engine):
@@ -67,9 +81,11 @@ def test_tunnel_points_mode_flat_pass(engine):
     flat = scans[:1].copy()
     from qdsim import FLAG_CARRY_ROWS
     z_ref, n_ref, gap = oracle_batch(mb, flat, FLAG_LATCH | FLAG_CARRY_ROWS)
-    bad = np.abs(n.reshape(16, 16, -1) - n_ref[0]).max(axis=-1) > N_ATOL
-    assert bad.mean() < 0.02
-    np.testing.assert_allclose(z.reshape(16, 16)[~bad], z_ref[0][~bad], rtol=1e-5, atol=1e-7)
+    _, n_free, _ = oracle_batch(mb, flat, 0)
+    explain_latched_mismatches(n.reshape(16, 16, -1), n_ref[0], n_free[0], gap[0], carry_rows=True)
+    same = np.abs(n.reshape(16, 16, -1) - n_ref[0]).max(axis=-1) <= N_ATOL
+    assert same.mean() > 0.5
+    _assert_z(z.reshape(1, 16, 16), z_ref, n.reshape(1, 16, 16, -1), n_ref, same[None], mb, flat)
 
 
 def test_tunnel_constant_tc_without_barriers(engine):
@@ -130,4 +146,4 @@ def test_tunnel_one_wide_sector(engine, n_dot):
     ok = gap.reshape(-1) > GAP_MIN
     assert ok.mean() > 0.8
     np.testing.assert_allclose(nn.reshape(-1, n)[ok], n_ref.reshape(-1, n)[ok], rtol=0, atol=N_ATOL)
-    np.testing.assert_allclose(z.reshape(-1)[ok], z_ref.reshape(-1)[ok], rtol=1e-5, atol=1e-7)
+    _assert_z(z.reshape(z_ref.shape), z_ref, nn.reshape(n_ref.shape), n_ref, ok.reshape(z_ref.shape), mb, s)
