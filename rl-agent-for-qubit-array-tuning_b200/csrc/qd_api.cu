@@ -124,6 +124,29 @@ kernel_fn pick_n(int n) {
   }
 }
 
+kernel_fn pick_fast(int n) {
+  switch (n) {
+    case 1: return qd::qd_scan_fast_kernel<1>;
+    case 2: return qd::qd_scan_fast_kernel<2>;
+    case 3: return qd::qd_scan_fast_kernel<3>;
+    case 4: return qd::qd_scan_fast_kernel<4>;
+    case 5: return qd::qd_scan_fast_kernel<5>;
+    case 6: return qd::qd_scan_fast_kernel<6>;
+    case 7: return qd::qd_scan_fast_kernel<7>;
+    case 8: return qd::qd_scan_fast_kernel<8>;
+    default: return nullptr;
+  }
+}
+
+// default / thresholded search with a hard argmin on affine windows runs the restructured kernel (qd_scan_fast_kernel);
+// QDSIM_GENERIC_SCAN=1 keeps the generic one (A/B timing, and the parity tests run both)
+bool use_fast_kernel(const qd_layout& L, unsigned flags, bool points) {
+  if (points || (flags & QD_FLAG_THERMAL)) return false;
+  if (L.algorithm != QD_ALG_DEFAULT && L.algorithm != QD_ALG_THRESHOLDED) return false;
+  const char* e = getenv("QDSIM_GENERIC_SCAN");
+  return !(e && e[0] == '1');
+}
+
 kernel_fn pick_tunnel_gs(int n) {
   switch (n) {
     case 2: return qd::qd_tunnel_gs_kernel<2>;
@@ -200,7 +223,8 @@ int mark_launch(qd_ctx* ctx, cudaStream_t stream) {
 // enqueue one launch over device-resident descriptors
 int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const double* d_points, float* d_z, void* d_n,
            int n_type, unsigned flags, cudaStream_t stream, int rows_cap = 0) {
-  kernel_fn fn = pick_kernel(ctx->L, flags, d_points != nullptr);
+  const bool fast = use_fast_kernel(ctx->L, flags, d_points != nullptr);
+  kernel_fn fn = fast ? pick_fast(ctx->L.n_dot) : pick_kernel(ctx->L, flags, d_points != nullptr);
   if (!fn) return fail(ctx, QD_ERR_UNSUPPORTED, "no kernel for n_dot=%d algorithm=%d", ctx->L.n_dot, ctx->L.algorithm);
   qd::KArgs a;
   a.nbar = nullptr;
@@ -244,11 +268,11 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   a.n_type = n_type;
   a.flags = flags;
   a.status = ctx->d_status;
-  a.slot_bytes = qd::qd_slot_bytes(ctx->L);
+  a.slot_bytes = fast ? qd::qd_fast_slot_bytes(ctx->L) : qd::qd_slot_bytes(ctx->L);
   // item = block of rows of one scan handled by one warp.  Large batches: one scan per warp (staging amortised over
   // the whole scan).  Small batches: split rows so that every SM gets work.  A flat (carry-rows) pass is sequential
   // over the whole scan by definition.
-  const long long target_items = (long long)ctx->sm_count * 12 * 4;
+  const long long target_items = (long long)ctx->sm_count * (fast ? 16 : 12) * 4;
   long long rows = ((long long)n_scan * max_ny) / target_items;
   if (rows < 1) rows = 1;
   if (rows > max_ny) rows = max_ny;

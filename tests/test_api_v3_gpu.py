@@ -197,3 +197,51 @@ def test_batched_env_observations_do_not_alias(engine):
     assert obs1["image"].data_ptr() != obs0["image"].data_ptr()
     assert torch.equal(obs0["image"], keep), "the previous observation was overwritten by the step"
     assert not torch.equal(obs1["image"], keep)
+
+
+@pytest.mark.parametrize("n_dot,alg", [(8, "default"), (4, "default"), (5, "thresholded"), (2, "default"), (3, "default"),
+                                       (6, "default"), (7, "thresholded")])
+def test_fast_and_generic_scan_kernels_agree(engine, n_dot, alg, monkeypatch):
+    """qd_scan_fast_kernel (the hot instantiation) against qd_scan_kernel on the same batch: identical charge maps, images
+    equal to fp32 rounding (the sensor's dot term is summed in a different order)."""
+    from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_F32, N_U8, synth
+    flags = FLAG_LATCH | FLAG_NOISE | FLAG_RADIAL
+    dev = synth.sample_devices(40, n_dot, seed=100 + n_dot)
+    mb = synth.model_batch(dev, algorithm=alg, threshold=0.7)
+    engine.set_models(mb)
+    scans = synth.env_step_scans(mb, dev, res=48, seed=200 + n_dot, offset_range=4.0)
+    scans["rad_mode"][::7] = 2                      # some windows replaced by pure noise
+    out = {}
+    for generic in ("1", "0"):
+        monkeypatch.setenv("QDSIM_GENERIC_SCAN", generic)
+        for fl in (flags, FLAG_LATCH, 0):
+            out[generic, fl] = engine.scan_open_host(scans, n_type=N_U8, flags=fl)
+        out[generic, "f32"] = engine.scan_open_host(scans, n_type=N_F32, flags=flags)
+    for fl in (flags, FLAG_LATCH, 0, "f32"):
+        zg, ng = out["1", fl]
+        zf, nf = out["0", fl]
+        assert np.array_equal(ng, nf), f"flags {fl}: {(ng != nf).any(axis=-1).sum()} pixels differ"
+        np.testing.assert_allclose(zf, zg, rtol=2e-7, atol=1e-7)
+
+
+def test_fast_kernel_flat_pass_and_wide_search(engine, monkeypatch):
+    """Carry-rows (one warp per scan) and a strongly coupled device where dominance decides nothing (the Gray walk runs all
+    2^N settings) through both kernels."""
+    from qdsim import FLAG_CARRY_ROWS, FLAG_LATCH, FLAG_NOISE, N_U8, synth
+    dev = synth.sample_devices(3, 6, seed=77)
+    dev["Cdd"] *= 4.0                               # strong inter-dot coupling: wide undecided sets
+    mb = synth.model_batch(dev)
+    engine.set_models(mb)
+    scans = synth.env_step_scans(mb, dev, res=40, seed=78, offset_range=1.0)
+    res = {}
+    for generic in ("1", "0"):
+        monkeypatch.setenv("QDSIM_GENERIC_SCAN", generic)
+        res[generic] = [engine.scan_open_host(scans, n_type=N_U8, flags=f)
+                        for f in (FLAG_LATCH | FLAG_NOISE | FLAG_CARRY_ROWS, FLAG_LATCH | FLAG_NOISE)]
+    for (zg, ng), (zf, nf) in zip(res["1"], res["0"]):
+        assert np.array_equal(ng, nf)
+        np.testing.assert_allclose(zf, zg, rtol=2e-7, atol=1e-7)
+    z_ref, n_ref, margin = oracle_batch(mb, scans, FLAG_LATCH | FLAG_NOISE)
+    safe = (margin > 1e-9).all(axis=2)
+    nf = res["0"][1][1].reshape(n_ref.shape)
+    assert (nf.astype(np.int64) == np.rint(n_ref).astype(np.int64))[safe].all()
