@@ -41,6 +41,10 @@ struct qd_ctx {
   size_t pts_cap = 0;
   double* d_nbar = nullptr;       // tunnel path: <n> of every pixel between the two launches
   size_t nbar_cap = 0;
+  unsigned char* d_tfloor = nullptr;   // tunnel path, split pipeline: floor(n_c) of the current chunk, 8 bytes per pixel
+  size_t tfloor_cap = 0;
+  unsigned long long* d_tkeys = nullptr;   // ... and its 32 kept basis states, 256 bytes per pixel
+  size_t tkeys_cap = 0;
   void* d_obs = nullptr;          // qd_scan_obs_host: compact (typed) observation images before the copy-back
   size_t obs_cap = 0;
   double* d_stats = nullptr;      // qd_scan_obs_host: per-env (p_low, p_high)
@@ -54,7 +58,8 @@ struct qd_ctx {
   cudaStream_t last_stream = nullptr; //   for a launch on ANOTHER stream only once this has fired
   bool have_last = false;
   bool staged_pending = false;    // an asynchronous H2D out of h_scans may still be in flight
-  const void* configured[64] = {nullptr};   // kernels whose shared-memory attributes are already set
+  const void* configured[64] = {nullptr};   // kernels whose shared-memory attributes are already set ...
+  size_t configured_smem[64] = {0};         // ... and the dynamic size they were set for
   int n_configured = 0;
   cudaEvent_t staged = nullptr;   // h_scans may be rewritten once this has fired
   cudaStream_t s_compute = nullptr, s_copy = nullptr;   // qd_scan_open_host: launches / result copies, overlapped
@@ -123,6 +128,23 @@ kernel_fn pick_n(int n) {
     default: return nullptr;
   }
 }
+
+#define QD_PICK_N(NAME, KERNEL)                                  \
+  kernel_fn NAME(int n) {                                        \
+    switch (n) {                                                 \
+      case 2: return qd::KERNEL<2>;                              \
+      case 3: return qd::KERNEL<3>;                              \
+      case 4: return qd::KERNEL<4>;                              \
+      case 5: return qd::KERNEL<5>;                              \
+      case 6: return qd::KERNEL<6>;                              \
+      case 7: return qd::KERNEL<7>;                              \
+      case 8: return qd::KERNEL<8>;                              \
+      default: return nullptr;                                   \
+    }                                                            \
+  }
+QD_PICK_N(pick_tunnel_relax, qd_tunnel_relax_kernel)
+QD_PICK_N(pick_tunnel_select, qd_tunnel_select_kernel)
+QD_PICK_N(pick_tunnel_eigen, qd_tunnel_eigen_kernel)
 
 kernel_fn pick_fast(int n) {
   switch (n) {
@@ -194,15 +216,17 @@ int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) 
 
 // shared-memory attributes of a kernel: set once per context (two driver calls saved per launch)
 int configure_kernel(qd_ctx* ctx, const void* fn, size_t smem) {
+  int at = -1;
   for (int i = 0; i < ctx->n_configured; ++i)
-    if (ctx->configured[i] == fn) return QD_OK;
-  // every slot size of a kernel is fixed by the model layout, which can change: ask for the architectural maximum once
-  (void)smem;
-  QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (ctx->configured[i] == fn) { at = i; break; }
+  if (at >= 0 && ctx->configured_smem[at] >= smem) return QD_OK;
+  if (smem > 48 * 1024 || at < 0)
+    QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
   // every warp stages its own record: ask for the largest shared-memory carveout so that registers, not shared
   // memory, bound the resident warps
-  QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  if (ctx->n_configured < 64) ctx->configured[ctx->n_configured++] = fn;
+  if (at < 0) QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  if (at < 0 && ctx->n_configured < 64) at = ctx->n_configured++;
+  if (at >= 0) { ctx->configured[at] = fn; ctx->configured_smem[at] = std::max<size_t>(smem, 48 * 1024); }
   return QD_OK;
 }
 
@@ -223,39 +247,114 @@ int mark_launch(qd_ctx* ctx, cudaStream_t stream) {
 // enqueue one launch over device-resident descriptors
 int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const double* d_points, float* d_z, void* d_n,
            int n_type, unsigned flags, cudaStream_t stream, int rows_cap = 0) {
+  {
+    const int rc0 = order_after_last_launch(ctx, stream);     // the scratch of an earlier launch on another stream
+    if (rc0) return rc0;
+  }
   const bool fast = use_fast_kernel(ctx->L, flags, d_points != nullptr);
   kernel_fn fn = fast ? pick_fast(ctx->L.n_dot) : pick_kernel(ctx->L, flags, d_points != nullptr);
   if (!fn) return fail(ctx, QD_ERR_UNSUPPORTED, "no kernel for n_dot=%d algorithm=%d", ctx->L.n_dot, ctx->L.algorithm);
   qd::KArgs a;
+  memset(&a, 0, sizeof(a));
   a.nbar = nullptr;
   if (ctx->L.algorithm == QD_ALG_TUNNEL) {
-    // launch 1 of 2: tunnel-coupled ground state, one warp per pixel, every pixel of every scan independent
-    kernel_fn gs = pick_tunnel_gs(ctx->L.n_dot);
-    if (!gs) return fail(ctx, QD_ERR_UNSUPPORTED, "tunnel path needs 2..8 dots, got %d", ctx->L.n_dot);
-    int rc = grow(ctx, &ctx->d_nbar, &ctx->nbar_cap, (size_t)ctx->up_pixels * ctx->L.n_dot * sizeof(double));
+    // tunnel-coupled ground state of every pixel into d_nbar, then (below) the scan kernel for latching / sensor / noise
+    const int N = ctx->L.n_dot;
+    kernel_fn gs = pick_tunnel_gs(N);
+    if (!gs) return fail(ctx, QD_ERR_UNSUPPORTED, "tunnel path needs 2..8 dots, got %d", N);
+    int rc = grow(ctx, &ctx->d_nbar, &ctx->nbar_cap, (size_t)ctx->up_pixels * N * sizeof(double));
     if (rc) return rc;
     qd::KArgs g;
+    memset(&g, 0, sizeof(g));
     g.L = ctx->L; g.records = ctx->d_records; g.scans = d_scans; g.points = d_points; g.z_out = nullptr;
     g.n_out = nullptr; g.nbar = ctx->d_nbar; g.n_scan = n_scan; g.n_type = QD_N_NONE; g.flags = flags;
     g.status = ctx->d_status;
-    g.slot_bytes = qd::qd_tunnel_slot_bytes(ctx->L);
     const long long max_pix = ctx->up_max_pix;
-    const long long want_items = (long long)ctx->sm_count * 12 * 4;
-    long long ppi = ((long long)n_scan * max_pix) / want_items;          // pixels per item
-    if (ppi < 1) ppi = 1;
-    if (ppi > 64) ppi = 64;
-    g.rows_per_item = (int)ppi;
-    g.items_per_scan = (int)((max_pix + ppi - 1) / ppi);
-    const long long items = (long long)n_scan * g.items_per_scan;
-    const int gw = (items < (long long)ctx->sm_count * 4) ? 1 : 4;
-    long long ggrid = (items + gw - 1) / gw;
-    if (ggrid > 0x7fffffffLL) ggrid = 0x7fffffffLL;
-    const size_t gsmem = (size_t)g.slot_bytes * gw;
-    rc = configure_kernel(ctx, (const void*)gs, gsmem);
-    if (rc) return rc;
-    gs<<<(unsigned)ggrid, gw * 32, gsmem, stream>>>(g);
-    QD_CUDA(ctx, cudaGetLastError());
-    ctx->launches += 1;
+    const char* mono_e = getenv("QDSIM_TUNNEL_MONO");
+    const bool mono = mono_e && mono_e[0] == '1';
+    if (mono) {
+      // the single-kernel form (one warp per pixel does everything): kept as the A/B reference of the split pipeline
+      g.slot_bytes = qd::qd_tunnel_slot_bytes(ctx->L);
+      const long long want_items = (long long)ctx->sm_count * 12 * 4;
+      long long ppi = ((long long)n_scan * max_pix) / want_items;          // pixels per item
+      if (ppi < 1) ppi = 1;
+      if (ppi > 64) ppi = 64;
+      g.rows_per_item = (int)ppi;
+      g.items_per_scan = (int)((max_pix + ppi - 1) / ppi);
+      const long long items = (long long)n_scan * g.items_per_scan;
+      const int gw = (items < (long long)ctx->sm_count * 4) ? 1 : 4;
+      long long ggrid = (items + gw - 1) / gw;
+      if (ggrid > 0x7fffffffLL) ggrid = 0x7fffffffLL;
+      const size_t gsmem = (size_t)g.slot_bytes * gw;
+      rc = configure_kernel(ctx, (const void*)gs, gsmem);
+      if (rc) return rc;
+      gs<<<(unsigned)ggrid, gw * 32, gsmem, stream>>>(g);
+      QD_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 1;
+    } else {
+      // split pipeline R -> S -> E over chunks of scans (8 + 256 bytes of scratch per pixel of a chunk)
+      kernel_fn kr = pick_tunnel_relax(N), ks = pick_tunnel_select(N), ke = pick_tunnel_eigen(N);
+      long long chunk_pix = 8LL << 20;
+      if (const char* e = getenv("QDSIM_TUNNEL_CHUNK_PIX")) chunk_pix = atoll(e) > 0 ? atoll(e) : chunk_pix;
+      long long spc = chunk_pix / max_pix;                                 // scans per chunk
+      if (spc < 1) spc = 1;
+      if (spc > n_scan) spc = n_scan;
+      rc = grow(ctx, &ctx->d_tfloor, &ctx->tfloor_cap, (size_t)spc * max_pix * 8);
+      if (rc) return rc;
+      rc = grow(ctx, &ctx->d_tkeys, &ctx->tkeys_cap, (size_t)spc * max_pix * 256);
+      if (rc) return rc;
+      g.tfloor = ctx->d_tfloor;
+      g.tkeys = ctx->d_tkeys;
+      g.tstride = max_pix;
+      for (long long c0 = 0; c0 < n_scan; c0 += spc) {
+        const int nc = (int)std::min<long long>(spc, n_scan - c0);
+        g.scans = d_scans + c0;
+        g.n_scan = nc;
+        // R: one thread per pixel, a CTA per <= 1024 pixels of one scan
+        {
+          qd::KArgs r = g;
+          r.rows_per_item = (int)std::min<long long>(1024, max_pix);
+          r.items_per_scan = (int)((max_pix + r.rows_per_item - 1) / r.rows_per_item);
+          long long grid = (long long)nc * r.items_per_scan;
+          if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+          const size_t smem = (size_t)qd::qd_tunnel_relax_smem_bytes(ctx->L);
+          rc = configure_kernel(ctx, (const void*)kr, smem);
+          if (rc) return rc;
+          kr<<<(unsigned)grid, 128, smem, stream>>>(r);
+          QD_CUDA(ctx, cudaGetLastError());
+        }
+        // S and E: one warp per pixel, items of <= 64 consecutive pixels (the warm start runs along an item)
+        const long long want_items = (long long)ctx->sm_count * 16 * 4;
+        long long ppi = ((long long)nc * max_pix) / want_items;
+        if (ppi < 1) ppi = 1;
+        if (ppi > 64) ppi = 64;
+        g.rows_per_item = (int)ppi;
+        g.items_per_scan = (int)((max_pix + ppi - 1) / ppi);
+        const long long items = (long long)nc * g.items_per_scan;
+        const int gw = (items < (long long)ctx->sm_count * 4) ? 1 : 4;
+        long long ggrid = (items + gw - 1) / gw;
+        if (ggrid > 0x7fffffffLL) ggrid = 0x7fffffffLL;
+        {
+          qd::KArgs sa = g;
+          sa.slot_bytes = qd::qd_tunnel_select_slot_bytes(ctx->L);
+          const size_t smem = (size_t)sa.slot_bytes * gw;
+          rc = configure_kernel(ctx, (const void*)ks, smem);
+          if (rc) return rc;
+          ks<<<(unsigned)ggrid, gw * 32, smem, stream>>>(sa);
+          QD_CUDA(ctx, cudaGetLastError());
+        }
+        {
+          qd::KArgs ea = g;
+          ea.slot_bytes = qd::qd_tunnel_eigen_slot_bytes(ctx->L);
+          const size_t smem = (size_t)ea.slot_bytes * gw;
+          rc = configure_kernel(ctx, (const void*)ke, smem);
+          if (rc) return rc;
+          ke<<<(unsigned)ggrid, gw * 32, smem, stream>>>(ea);
+          QD_CUDA(ctx, cudaGetLastError());
+        }
+        ctx->launches += 3;
+      }
+    }
     a.nbar = ctx->d_nbar;
   }
   a.L = ctx->L;
@@ -521,6 +620,8 @@ void qd_destroy(qd_ctx* ctx) {
   if (ctx->d_n) cudaFree(ctx->d_n);
   if (ctx->d_pts) cudaFree(ctx->d_pts);
   if (ctx->d_nbar) cudaFree(ctx->d_nbar);
+  if (ctx->d_tfloor) cudaFree(ctx->d_tfloor);
+  if (ctx->d_tkeys) cudaFree(ctx->d_tkeys);
   if (ctx->d_obs) cudaFree(ctx->d_obs);
   if (ctx->d_stats) cudaFree(ctx->d_stats);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);

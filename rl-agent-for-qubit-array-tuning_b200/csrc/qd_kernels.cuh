@@ -36,6 +36,11 @@ struct KArgs {
   void* __restrict__ n_out;
   double* __restrict__ nbar;           // tunnel path: <n> per pixel, [pixels, N] (written by qd_tunnel_gs_kernel)
   unsigned* status;                    // sticky QD_STATUS_* word (host-mapped): written only when something is wrong
+  // tunnel path, split pipeline (qd_tunnel_relax / select / eigen kernels): per-pixel scratch of the current chunk of
+  // scans, addressed by (scan index inside the chunk) * tstride + pixel
+  unsigned char* tfloor;               // [slots][8]   floor of the relaxed continuous occupations
+  unsigned long long* tkeys;           // [slots][32]  the 32 kept basis states, 8 bits per dot
+  long long tstride;                   // pixels per scan slot (largest scan of the upload)
   int n_scan;
   int n_type;
   unsigned flags;

@@ -147,3 +147,40 @@ def test_tunnel_one_wide_sector(engine, n_dot):
     assert ok.mean() > 0.8
     np.testing.assert_allclose(nn.reshape(-1, n)[ok], n_ref.reshape(-1, n)[ok], rtol=0, atol=N_ATOL)
     _assert_z(z.reshape(z_ref.shape), z_ref, nn.reshape(n_ref.shape), n_ref, ok.reshape(z_ref.shape), mb, s)
+
+
+@pytest.mark.parametrize("n_dot,res,n_env", [(4, 24, 3), (6, 16, 2), (8, 12, 2), (2, 16, 1), (3, 16, 1)])
+def test_split_pipeline_equals_monolithic_kernel(engine, n_dot, res, n_env, monkeypatch):
+    """The three-kernel pipeline (relax / select / eigen) against the single-kernel form it was cut from: the same 32 states
+    and the same solver, so <n> agrees far inside the solver tolerance (the relaxation's summation order differs)."""
+    from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, N_F64
+    dev, mb, scans = _setup(engine, n_dot, n_env, res, seed=90 + n_dot)
+    scans["rad_mode"][::3] = 2
+    flags = FLAG_LATCH | FLAG_NOISE | FLAG_RADIAL
+    out = {}
+    for mono in ("1", "0"):
+        monkeypatch.setenv("QDSIM_TUNNEL_MONO", mono)
+        out[mono] = engine.scan_open_host(scans, n_type=N_F64, flags=0), engine.scan_open_host(scans, n_type=N_F64, flags=flags)
+    _, _, gap = oracle_batch(mb, scans, 0)
+    ok = gap.reshape(-1) > GAP_MIN
+    (z1, n1), (z1f, n1f) = out["1"]
+    (z0, n0), (z0f, n0f) = out["0"]
+    assert np.isfinite(n0).all() and np.isfinite(z0).all()
+    np.testing.assert_allclose(n0[ok], n1[ok], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(z0[ok], z1[ok], rtol=1e-7, atol=1e-9)
+    same = np.abs(n0f - n1f).max(axis=-1) <= 1e-9
+    assert same.mean() > 0.97
+    np.testing.assert_allclose(z0f[same], z1f[same], rtol=1e-6, atol=1e-8)
+
+
+def test_split_pipeline_chunking(engine, monkeypatch):
+    """More scans than one scratch chunk holds (QDSIM_TUNNEL_CHUNK_PIX): chunk boundaries must not show."""
+    from qdsim import FLAG_LATCH, FLAG_NOISE, N_F64
+    dev, mb, scans = _setup(engine, 4, 6, 32, seed=97)                      # 18 scans of 1024 pixels
+    flags = FLAG_LATCH | FLAG_NOISE
+    z_all, n_all = engine.scan_open_host(scans, n_type=N_F64, flags=flags)
+    for pix in ("2048", "5000", "1"):                                       # 2, 4 and 1 scans per chunk
+        monkeypatch.setenv("QDSIM_TUNNEL_CHUNK_PIX", pix)
+        z, n = engine.scan_open_host(scans, n_type=N_F64, flags=flags)
+        np.testing.assert_array_equal(n, n_all)
+        np.testing.assert_array_equal(z, z_all)
