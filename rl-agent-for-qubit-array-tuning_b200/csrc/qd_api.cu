@@ -843,23 +843,41 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   return check_status(ctx);
 }
 
+extern "C++" {
 namespace {
 size_t z_elem_size(int z_type) { return z_type == QD_Z_F32 ? 4 : z_type == QD_Z_F16 ? 2 : z_type == QD_Z_U8 ? 1 : 0; }
 
-int normalise_typed(qd_ctx* ctx, const float* z, void* out, int z_type, int64_t per_env, int n_env, double q_low_pct,
-                    double q_high_pct, double* stats, cudaStream_t stream) {
-  const double ql = q_low_pct / 100.0, qh = q_high_pct / 100.0;
-  switch (z_type) {
-    case QD_Z_F32: qd::qd_normalise_kernel<float><<<n_env, 512, 0, stream>>>(z, (float*)out, per_env, n_env, ql, qh, stats); break;
-    case QD_Z_F16: qd::qd_normalise_kernel<__half><<<n_env, 512, 0, stream>>>(z, (__half*)out, per_env, n_env, ql, qh, stats); break;
-    case QD_Z_U8: qd::qd_normalise_kernel<unsigned char><<<n_env, 512, 0, stream>>>(z, (unsigned char*)out, per_env, n_env, ql, qh, stats); break;
-    default: return fail(ctx, QD_ERR_INVALID, "bad z_type %d", z_type);
+template <typename OUT>
+int normalise_launch(qd_ctx* ctx, const float* z, OUT* out, int64_t per_env, int n_env, double ql, double qh, double* stats,
+                     cudaStream_t stream) {
+  const size_t need = (size_t)per_env * sizeof(float);
+  if (need <= 200 * 1024) {          // the env's image fits in shared memory: one HBM read per pixel
+    auto fn = qd::qd_normalise_kernel<OUT, true>;
+    if (need > 40 * 1024) {
+      int rc = configure_kernel(ctx, (const void*)fn, need);
+      if (rc) return rc;
+    }
+    fn<<<n_env, 1024, need, stream>>>(z, out, per_env, n_env, ql, qh, stats);
+  } else {
+    qd::qd_normalise_kernel<OUT, false><<<n_env, 1024, 0, stream>>>(z, out, per_env, n_env, ql, qh, stats);
   }
   QD_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
   return QD_OK;
 }
+
+int normalise_typed(qd_ctx* ctx, const float* z, void* out, int z_type, int64_t per_env, int n_env, double q_low_pct,
+                    double q_high_pct, double* stats, cudaStream_t stream) {
+  const double ql = q_low_pct / 100.0, qh = q_high_pct / 100.0;
+  switch (z_type) {
+    case QD_Z_F32: return normalise_launch<float>(ctx, z, (float*)out, per_env, n_env, ql, qh, stats, stream);
+    case QD_Z_F16: return normalise_launch<__half>(ctx, z, (__half*)out, per_env, n_env, ql, qh, stats, stream);
+    case QD_Z_U8: return normalise_launch<unsigned char>(ctx, z, (unsigned char*)out, per_env, n_env, ql, qh, stats, stream);
+    default: return fail(ctx, QD_ERR_INVALID, "bad z_type %d", z_type);
+  }
+}
 }  // namespace
+}  // extern "C++"
 
 int qd_scan_obs_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, int scans_per_env, void* out_host, int z_type,
                      int normalise, double q_low_pct, double q_high_pct, double* stats_host, unsigned flags) {

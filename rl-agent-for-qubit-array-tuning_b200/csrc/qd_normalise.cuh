@@ -4,8 +4,8 @@
 //     image = clip((image - p_low) / (p_high - p_low), 0, 1).astype(float32)      # zeros if p_high <= p_low
 // One CTA per env.  The four order statistics the two interpolated percentiles need (ranks k, k+1 at both ends) are
 // found EXACTLY by a 4-pass 8-bit radix select over the monotone uint32 image of the fp32 values (shared-memory
-// histograms, four ranks tracked at once), then one more pass normalises in fp64 and writes fp32.  HBM-bound:
-// 5 reads + 1 write of 4 B per pixel.
+// histograms, four ranks tracked at once), then one more pass normalises in fp64 and writes fp32 / half / uint8.  The
+// env's image (N-1 scans, 112 KB at 8 dots x 64 x 64) is staged in shared memory once: 4 B read + one typed write per pixel.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -32,16 +32,34 @@ __device__ __forceinline__ void store_norm(float* p, double v) { *p = (float)v; 
 __device__ __forceinline__ void store_norm(__half* p, double v) { *p = __float2half_rn((float)v); }
 __device__ __forceinline__ void store_norm(unsigned char* p, double v) { *p = (unsigned char)__double2int_rn(255.0 * v); }
 
-template <typename OUT>
-__global__ void __launch_bounds__(512) qd_normalise_kernel(const float* __restrict__ z, OUT* __restrict__ out,
-                                                           long long per_env, int n_env, double q_lo, double q_hi,
-                                                           double* __restrict__ stats) {
+// One histogram update per distinct bin of the warp instead of one shared-memory atomic per lane: the top bytes of a
+// sensor image fall into two or three bins, where 32 same-address atomics would serialise.
+__device__ __forceinline__ void hist_add(unsigned* hist, uint32_t b, bool on) {
+  const unsigned act = __ballot_sync(0xffffffffu, on);
+  if (!on) return;
+  const unsigned peers = __match_any_sync(act, b);
+  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[b], (unsigned)__popc(peers));
+}
+
+// RESIDENT = true: the env's image is staged in shared memory once (dynamic smem of per_env floats) and the four radix
+// passes + the output pass read it from there: 4 B read + sizeof(OUT) written per pixel of HBM traffic.
+template <typename OUT, bool RESIDENT>
+__global__ void __launch_bounds__(1024) qd_normalise_kernel(const float* __restrict__ z, OUT* __restrict__ out,
+                                                            long long per_env, int n_env, double q_lo, double q_hi,
+                                                            double* __restrict__ stats) {
+  extern __shared__ __align__(16) float zs[];
   __shared__ unsigned hist[4][256];
   __shared__ uint32_t prefix[4];
   __shared__ long long rank[4];
   const int env = blockIdx.x;
   if (env >= n_env) return;
-  const float* __restrict__ src = z + (size_t)env * per_env;
+  const float* __restrict__ gsrc = z + (size_t)env * per_env;
+  const long long n_round = (per_env + 31) & ~31LL;          // whole warps run every iteration (match / ballot below)
+  if (RESIDENT) {
+    for (long long i = threadIdx.x; i < per_env; i += blockDim.x) zs[i] = gsrc[i];
+    __syncthreads();
+  }
+  const float* __restrict__ src = RESIDENT ? zs : gsrc;
   // numpy 'linear' percentile: virtual index (n-1) q, neighbours floor / floor+1 (clamped), weight = fractional part
   const double vi_lo = (double)(per_env - 1) * q_lo, vi_hi = (double)(per_env - 1) * q_hi;
   const long long k_lo = (long long)floor(vi_lo), k_hi = (long long)floor(vi_hi);
@@ -58,15 +76,16 @@ __global__ void __launch_bounds__(512) qd_normalise_kernel(const float* __restri
     const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
     const uint32_t p0 = prefix[0], p1 = prefix[1], p2 = prefix[2], p3 = prefix[3];
     // ranks that still share their prefix share one histogram (all four in the first pass, usually the two of each end
-    // afterwards): count once, copy after the pass -- a quarter / half of the shared-memory atomics
+    // afterwards): count once, copy after the pass
     const bool d1 = p1 != p0, d2 = p2 != p0 && p2 != p1, d3 = p3 != p0 && p3 != p1 && p3 != p2;
-    for (long long i = threadIdx.x; i < per_env; i += blockDim.x) {
-      const uint32_t k = f32_key(src[i]);
+    for (long long i = threadIdx.x; i < n_round; i += blockDim.x) {
+      const bool in = i < per_env;
+      const uint32_t k = in ? f32_key(src[i]) : 0u;
       const uint32_t b = (k >> shift) & 0xffu, top = k & hi_mask;
-      if (top == p0) atomicAdd(&hist[0][b], 1u);
-      if (d1 && top == p1) atomicAdd(&hist[1][b], 1u);
-      if (d2 && top == p2) atomicAdd(&hist[2][b], 1u);
-      if (d3 && top == p3) atomicAdd(&hist[3][b], 1u);
+      hist_add(hist[0], b, in && top == p0);
+      if (d1) hist_add(hist[1], b, in && top == p1);
+      if (d2) hist_add(hist[2], b, in && top == p2);
+      if (d3) hist_add(hist[3], b, in && top == p3);
     }
     __syncthreads();
     if (threadIdx.x < 256) {
