@@ -717,6 +717,24 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
       r[L.o_spos + j] = sp;
       r[L.o_sneg + j] = sn;
     }
+    if (alg == QD_ALG_BRUTE_FORCE) {
+      // cdd_inv = U D U^T, U unit upper triangular (the branch-and-bound order of ground_state_brute: dot 0 outermost)
+      double* d = r + L.o_ud;
+      double* U = r + L.o_ud + 8;
+      const double* Cm = r + L.o_cinv;
+      for (int k = N - 1; k >= 0; --k) {
+        double dk = Cm[k * N + k];
+        for (int j = k + 1; j < N; ++j) dk -= U[k * N + j] * U[k * N + j] * d[j];
+        if (!(dk > 0.0)) return fail(ctx, QD_ERR_INVALID, "env %d: cdd_inv is not positive definite", e);
+        d[k] = dk;
+        U[k * N + k] = 1.0;
+        for (int i = 0; i < k; ++i) {
+          double u = Cm[i * N + k];
+          for (int j = k + 1; j < N; ++j) u -= U[i * N + j] * U[k * N + j] * d[j];
+          U[i * N + k] = u / dk;
+        }
+      }
+    }
     if (alg == QD_ALG_TUNNEL) {
       if (cbg && NV > G) memcpy(r + L.o_cbg, cbg + (size_t)e * (NV - G) * G, sizeof(double) * (NV - G) * G);
     }

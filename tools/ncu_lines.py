@@ -11,8 +11,14 @@ from collections import defaultdict
 
 
 def load(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
-                         capture_output=True, text=True).stdout
+    if rep.endswith(".gz"):                          # a source-page CSV exported on the GPU box (the .ncu-rep stays there)
+        import gzip
+        out = gzip.open(rep, "rt").read()
+    elif rep.endswith(".csv"):
+        out = open(rep).read()
+    else:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
+                             capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     per = defaultdict(lambda: [0, 0, ""])           # (file, line) -> [inst, samples, text]
     cur_file, cur_line = None, None
