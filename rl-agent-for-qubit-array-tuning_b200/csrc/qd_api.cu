@@ -246,7 +246,7 @@ int mark_launch(qd_ctx* ctx, cudaStream_t stream) {
 
 // enqueue one launch over device-resident descriptors
 int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const double* d_points, float* d_z, void* d_n,
-           int n_type, unsigned flags, cudaStream_t stream, int rows_cap = 0) {
+           int n_type, unsigned flags, cudaStream_t stream, int rows_cap = 0, const qd_scan* h_one = nullptr) {
   {
     const int rc0 = order_after_last_launch(ctx, stream);     // the scratch of an earlier launch on another stream
     if (rc0) return rc0;
@@ -367,6 +367,7 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   a.n_type = n_type;
   a.flags = flags;
   a.status = ctx->d_status;
+  if (h_one && ctx->L.algorithm != QD_ALG_TUNNEL) { a.use_one = 1; a.one = *h_one; }
   a.slot_bytes = fast ? qd::qd_fast_slot_bytes(ctx->L) : qd::qd_slot_bytes(ctx->L);
   // item = block of rows of one scan handled by one warp.  Large batches: one scan per warp (staging amortised over
   // the whole scan).  Small batches: split rows so that every SM gets work.  A flat (carry-rows) pass is sequential
@@ -793,13 +794,27 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   if (rc) return rc;
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
   int max_ny = 0;
-  rc = stage_scans(ctx, n_scan, scans, ctx->s_compute, &max_ny, true);
-  if (rc) return rc;
+  // one scan of a Path A model (a single do2d_open): the descriptor goes into the kernel parameters, no H2D copy
+  const bool one = n_scan == 1 && scans && ctx->L.algorithm != QD_ALG_TUNNEL && scans[0].pix_offset == 0 &&
+                   (long long)scans[0].nx * scans[0].ny * (4 + ctx->L.n_dot * (long long)n_elem_size(n_type)) <= (1 << 20);
+  if (one) {
+    const qd_scan& s0 = scans[0];
+    if (s0.env_id < 0 || s0.env_id >= ctx->n_env)
+      return fail(ctx, QD_ERR_INVALID, "scan 0: env_id %d out of range [0,%d)", s0.env_id, ctx->n_env);
+    if (s0.nx <= 0 || s0.ny <= 0) return fail(ctx, QD_ERR_INVALID, "scan 0: nx, ny must be positive");
+    rc = order_after_last_launch(ctx, ctx->s_compute);
+    if (rc) return rc;
+    max_ny = s0.ny;
+    ctx->up_n_scan = 0;                 // nothing resident for qd_scan_launch
+    ctx->up_max_ny = s0.ny;
+    ctx->up_pixels = ctx->up_max_pix = (long long)s0.nx * s0.ny;
+  } else {
+    rc = stage_scans(ctx, n_scan, scans, ctx->s_compute, &max_ny, true);
+    if (rc) return rc;
+  }
   const long long pixels = ctx->up_pixels;
   const int N = ctx->L.n_dot;
   const size_t esz = n_elem_size(n_type);
-  const size_t zbytes = z_out_host ? (size_t)pixels * sizeof(float) : 0, nbytes = (size_t)pixels * N * esz;
-
   // ---- small calls (a single do2d_open): the kernel writes its outputs straight into mapped pinned host memory, so the
   // call is one descriptor copy, one launch (two on the tunnel path) and one synchronisation -- no device-to-host copies
   if (zbytes + nbytes <= (1u << 20) && n_scan <= 64) {
@@ -817,7 +832,7 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
     for (int i = 0; i < n_scan; ++i) sum += (long long)scans[i].nx * scans[i].ny;
     if (sum != pixels) memset(ctx->h_small, 0, need);          // gaps between scans read as zeros
     rc = launch(ctx, n_scan, ctx->d_scans, max_ny, nullptr, z_out_host ? (float*)ctx->d_small : nullptr,
-                ctx->d_small + zoff, n_type, flags, ctx->s_compute);
+                ctx->d_small + zoff, n_type, flags, ctx->s_compute, 0, one ? scans : nullptr);
     if (rc) return rc;
     QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
     ctx->staged_pending = false;

@@ -41,6 +41,10 @@ struct KArgs {
   unsigned char* tfloor;               // [slots][8]   floor of the relaxed continuous occupations
   unsigned long long* tkeys;           // [slots][32]  the 32 kept basis states, 8 bits per dot
   long long tstride;                   // pixels per scan slot (largest scan of the upload)
+  // single-scan fast path (one do2d_open): the descriptor travels in the kernel parameters instead of through a
+  // host-to-device copy; `scans` is then unused
+  int use_one;
+  qd_scan one;
   int n_scan;
   int n_type;
   unsigned flags;
@@ -694,7 +698,18 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
     const qd_scan* gscan = a.scans + scan_id;
 
     // ---- stage record + scan descriptor (TMA bulk, one mbarrier) ----
-    if (lane == 0) {
+    if (a.use_one) {
+      // the one descriptor of a single-scan call sits in the kernel parameters: lanes copy it, TMA brings the record
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, rec_bytes);
+        tma_bulk_g2s(rec, a.records + (size_t)a.one.env_id * L.rec_doubles, rec_bytes, bar);
+      }
+      const double* src = reinterpret_cast<const double*>(&a.one);
+      double* dst = reinterpret_cast<double*>(sc);
+      for (int i = lane; i < (int)(sizeof(qd_scan) / 8); i += 32) dst[i] = src[i];
+      __syncwarp();
+    } else if (lane == 0) {
       const int env = gscan->env_id;
       fence_proxy_async();
       mbar_expect_tx(bar, rec_bytes + (uint32_t)sizeof(qd_scan));
@@ -1073,7 +1088,18 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_FAST_MIN_BLOCKS) qd_scan
     const qd_scan* gscan = a.scans + scan_id;
 
     // ---- stage record + scan descriptor (TMA bulk, one mbarrier) ----
-    if (lane == 0) {
+    if (a.use_one) {
+      // the one descriptor of a single-scan call sits in the kernel parameters: lanes copy it, TMA brings the record
+      if (lane == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, rec_bytes);
+        tma_bulk_g2s(rec, a.records + (size_t)a.one.env_id * L.rec_doubles, rec_bytes, bar);
+      }
+      const double* src = reinterpret_cast<const double*>(&a.one);
+      double* dst = reinterpret_cast<double*>(sc);
+      for (int i = lane; i < (int)(sizeof(qd_scan) / 8); i += 32) dst[i] = src[i];
+      __syncwarp();
+    } else if (lane == 0) {
       const int env = gscan->env_id;
       fence_proxy_async();
       mbar_expect_tx(bar, rec_bytes + (uint32_t)sizeof(qd_scan));

@@ -114,11 +114,34 @@ class ChargeSensedDotArray:
     # ---- reference API -------------------------------------------------------------------------------------
     def do2d_open(self, x_gate, x_min, x_max, x_points, y_gate, y_min, y_max, y_points):
         """2-d sweep, open array.  Returns ``(z (y, x, n_sensor), n (y, x, n_dot))``."""
-        v0, dx, dy = self.gate_voltage_composer.affine2d(x_gate, x_min, x_max, x_points, y_gate, y_min, y_max, y_points)
-        s = self._scan_record()
-        s["v0"][0, :self.n_gate], s["dx"][0, :self.n_gate], s["dy"][0, :self.n_gate] = v0, dx, dy
+        # One persistent descriptor per model object; a sweep of PHYSICAL gates (what the facade's non-barrier mode calls,
+        # qarray_base_class.py:128-137) does not depend on the virtual gate matrix, so its affine form is cached by
+        # arguments -- this call is latency-bound (BASELINE config 1), every microsecond of host work shows.
+        d = self.__dict__
+        s = d.get("_scan1")
+        if s is None:
+            s = d["_scan1"] = new_scans(1)
+            d["_scan1_views"] = (s["v0"][0], s["dx"][0], s["dy"][0])
+            d["_affine_cache"] = {}
+        key = (x_gate, x_min, x_max, x_points, y_gate, y_min, y_max, y_points)
+        aff = d["_affine_cache"].get(key)
+        if aff is None:
+            aff = self.gate_voltage_composer.affine2d(x_gate, x_min, x_max, x_points, y_gate, y_min, y_max, y_points)
+            physical = all(isinstance(g, (int, np.integer)) or (isinstance(g, str) and not g.startswith("v"))
+                           for g in (x_gate, y_gate))
+            if physical:
+                if len(d["_affine_cache"]) > 64:
+                    d["_affine_cache"].clear()
+                d["_affine_cache"][key] = aff
+        ng = self.n_gate
+        v0v, dxv, dyv = d["_scan1_views"]
+        v0v[:ng], dxv[:ng], dyv[:ng] = aff
+        flags = self._flags(True)
+        s["peak_width"] = float(self.coulomb_peak_width)
         s["nx"], s["ny"] = x_points, y_points
-        z, n = engine_for(self, self.device).scan_open_host(s, n_type=N_F64, flags=self._flags(True))
+        if flags:                                   # the seed only feeds latching / noise draws
+            s["seed"] = fresh_seed()
+        z, n = engine_for(self, self.device).scan_one_host(s, N_F64, flags)
         return (z.astype(np.float64).reshape(y_points, x_points, 1), n.reshape(y_points, x_points, self.n_dot))
 
     def do1d_open(self, gate, min, max, points):  # noqa: A002

@@ -207,6 +207,18 @@ class Engine:
         self._check(self._lib.qd_scan_open_host(self._ctx, len(scans), _ptr(scans), _ptr(z), _ptr(n), n_type, flags))
         return z, n
 
+    def scan_one_host(self, scan: np.ndarray, n_type: int = N_F64, flags: int = 0):
+        """One scan window (a single ``do2d_open``), minimal host overhead: ``scan`` is a 1-element ``SCAN_DTYPE`` array with
+        ``pix_offset == 0``; returns fresh ``(z float32 [ny * nx], n [ny * nx, N])``.  The library takes its single-scan
+        path: descriptor in the kernel parameters, outputs written straight into mapped pinned memory, one sync."""
+        pixels = int(scan["nx"][0]) * int(scan["ny"][0])
+        z = np.empty(pixels, dtype=np.float32)
+        n = np.empty((pixels, self.models.n_dot), dtype=N_DTYPES[n_type])
+        rc = self._lib.qd_scan_open_host(self._ctx, 1, scan.ctypes.data, z.ctypes.data, n.ctypes.data, n_type, flags)
+        if rc != 0:
+            self._check(rc)
+        return z, n
+
     def scan_obs_host(self, scans: np.ndarray, z_type: int = Z_U8, flags: int = 0, normalise: bool = True,
                       q_low: float = 0.5, q_high: float = 99.5, out: np.ndarray | None = None, want_stats: bool = False,
                       scans_per_env: int | None = None):

@@ -39,8 +39,7 @@ def engine_for(model, device: int | None = None) -> Engine:
 def fresh_seed() -> int:
     """A 64-bit scan seed drawn from the process-global ``np.random`` state -- the stream the reference's noise and
     latching classes consume -- so ``np.random.seed(...)`` makes a run reproducible."""
-    hi, lo = np.random.randint(0, 2 ** 32, size=2, dtype=np.uint64)
-    return int((hi << np.uint64(32)) | lo)
+    return int.from_bytes(np.random.bytes(8), "little")
 
 
 def shutdown():

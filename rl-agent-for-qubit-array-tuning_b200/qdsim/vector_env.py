@@ -55,6 +55,14 @@ class EnvConfig:
     nearest_neighbour: bool = False             # CNN outputs [RL, LR] instead of [NN, NNN_right, NNN_left] (:62)
     variance_threshold: float = 0.05            # :65
     process_noise: float = 0.0                  # :66
+    # Which simulator sits under the shell.  True (every shipped env config; env.py:61-62 refuses anything else): the
+    # tunnel-coupled TunnelCoupledChargeSensed path.  False: the constant-interaction ChargeSensedDotArray path
+    # (QarrayBaseClass(use_barriers=False)) with `algorithm` in default / thresholded / brute_force -- BASELINE config 3
+    # ("6-dot ... brute-force ground-state search and Kalman virtualisation in the loop"); there are no barrier gates
+    # then: barrier actions are ignored and barrier rewards are zero.
+    use_barriers: bool = True
+    algorithm: str = "default"
+    max_charge_carriers: int = 4
 
 
 def gate_reward(dist, cfg: EnvConfig):
@@ -121,8 +129,13 @@ class BatchedDeviceEnv:
     def _sample(self):
         E, N, cfg = self.n_env, self.num_dots, self.cfg
         rng = self.rng
-        self.dev = synth.sample_barrier_devices(E, N, seed=int(rng.integers(0, 2 ** 31)))
-        self.mb = synth.tunnel_batch(self.dev)
+        if cfg.use_barriers:
+            self.dev = synth.sample_barrier_devices(E, N, seed=int(rng.integers(0, 2 ** 31)))
+            self.mb = synth.tunnel_batch(self.dev)
+        else:
+            self.dev = synth.sample_devices(E, N, seed=int(rng.integers(0, 2 ** 31)))
+            self.mb = synth.model_batch(self.dev, algorithm=cfg.algorithm, thermal=False,
+                                        max_charge_carriers=cfg.max_charge_carriers)
         self.window_delta = rng.uniform(*cfg.window_delta_range, size=E)
         rn = cfg.radial_noise
         self.radial = None
@@ -148,9 +161,13 @@ class BatchedDeviceEnv:
         if getattr(self, "_gt_phys_of", None) is not self.mb:     # physical optimum: a property of the device, per episode
             target = np.concatenate([np.full(N, cfg.optimal_vg_center[0]), [cfg.optimal_vg_center[1]]])
             vg_phys = maxwell.optimal_vg(self.mb.cdd_inv_full, self.mb.cgd_full[:, :, :G], target)          # (E, G)
-            tc_ratio = cfg.optimal_tc / self.dev["tc_base"]
-            vb_base = -np.log(tc_ratio)[:, None] / self.dev["alpha"]
-            self._gt_phys = (vg_phys, vb_base - np.einsum("ebg,eg->eb", self.dev["Cbg"], vg_phys))
+            if cfg.use_barriers:
+                tc_ratio = cfg.optimal_tc / self.dev["tc_base"]
+                vb_base = -np.log(tc_ratio)[:, None] / self.dev["alpha"]
+                vb_gt = vb_base - np.einsum("ebg,eg->eb", self.dev["Cbg"], vg_phys)
+            else:
+                vb_gt = np.zeros((self.n_env, N - 1))
+            self._gt_phys = (vg_phys, vb_gt)
             self._gt_phys_of = self.mb
         vg_phys, vb = self._gt_phys
         vg_virtual = np.linalg.solve(self.vgm, (vg_phys - self.origin)[..., None])[..., 0]
@@ -174,7 +191,8 @@ class BatchedDeviceEnv:
         seeds = ((np.uint64(self.seed) << np.uint64(44)) + (np.uint64(self._episode) << np.uint64(32))
                  + (np.uint64(self.step_count) << np.uint64(20)) + np.arange(self.n_env * (self.num_dots - 1), dtype=np.uint64))
         return obs.obs_scans(self.mb, self.gate_v, self.sensor_gt, self.vgm, self.origin, -self.window_delta,
-                             self.window_delta, res, barrier_voltages=self.barrier_v, peak_width=self.dev["peak_width"],
+                             self.window_delta, res, barrier_voltages=self.barrier_v if self.cfg.use_barriers else None,
+                             peak_width=self.dev["peak_width"],
                              gate_ground_truth=self.gate_gt if self.radial else None, radial=self.radial, seeds=seeds)
 
     def _reward(self):
@@ -182,6 +200,8 @@ class BatchedDeviceEnv:
         N = self.num_dots
         cgd_diag = np.abs(self.mb.cgd_full[:, np.arange(N), np.arange(N)])
         gate_d = np.abs(self.gate_gt - self.gate_v) * cgd_diag
+        if not self.cfg.use_barriers:
+            return {"gates": gate_reward(gate_d, self.cfg), "barriers": np.zeros((self.n_env, N - 1))}
         barrier_d = np.abs(self.barrier_gt - self.barrier_v) * self.dev["alpha"]
         return {"gates": gate_reward(gate_d, self.cfg), "barriers": barrier_reward(barrier_d, self.cfg)}
 

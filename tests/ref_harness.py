@@ -40,6 +40,9 @@ class OracleEngine:
         self.launch_count += 1
         return oscan.simulate_scan(m, s, **kw) if affine else oscan.simulate_points(m, v, s, **kw)
 
+    def scan_one_host(self, scan, n_type=3, flags=0):
+        return self.scan_open_host(scan, n_type=n_type, flags=flags)
+
     def scan_open_host(self, scans, n_type=1, flags=0, want_z=True, z_out=None, n_out=None):
         zs, ns = [], []
         for rec in scans:

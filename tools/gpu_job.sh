@@ -1,0 +1,17 @@
+#!/bin/bash
+# tools/gpu_job.sh TAG -- the standard measurement job of one gpurun call: GPU tests, bench, ncu captures (exported as CSV)
+tag=${1:-r02x}
+o=gpurun_out
+python -c "import bench; print(bench.source_sha())" > $o/sha_$tag.txt
+python -m pytest tests -m gpu -q 2>&1 | tail -150 > $o/${tag}_pytest.txt; tail -3 $o/${tag}_pytest.txt
+python bench.py > $o/${tag}_bench.json 2> $o/${tag}_bench.err; head -c 200 $o/${tag}_bench.json; echo
+B="python bench.py --n-env 2048 --steps 2 --warmup 1 --no-path-b --no-cpu-baseline --no-compact --parity-scans 0"
+$B > $o/${tag}_plainA.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:qd_scan_fast -s 3 -c 1 -o $o/prof_${tag}_fast8 $B > $o/${tag}_ncuA.log 2>&1
+T="python tools/tunnel_time.py --cases 8:64 --steps 1"
+$T > $o/${tag}_plainB.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $o/${tag}_launches_tunnel.csv $T > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_select -s 2 -c 1 -o $o/prof_${tag}_select8 $T > $o/${tag}_ncuS.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_eigen -s 2 -c 1 -o $o/prof_${tag}_eigen8 $T > $o/${tag}_ncuE.log 2>&1
+tools/ncu_export.sh $o/prof_${tag}_fast8 $o/prof_${tag}_select8 $o/prof_${tag}_eigen8
+python tools/sweep.py --quick > $o/${tag}_sweep_quick.json 2> $o/${tag}_sweep.err
+python tools/shell_breakdown.py > $o/${tag}_shell_breakdown.txt 2>&1
+du -sh $o

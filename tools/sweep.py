@@ -182,6 +182,30 @@ def main():
     c3["cpu_brute_force"] = time_cpu(mb, sc[:64], budget_s=3.0)
     mbd = synth.model_batch(dev, algorithm="default")
     c3["path_A_default_same_devices"] = time_gpu(eng, mbd, sc, N_U8)
+    # ... and as BASELINE states it: brute-force search AND Kalman virtualisation in the loop -- the batched env shell on
+    # Path A brute_force models, CNN forward + scalar Kalman filter + batched VGM update after every observation
+    from qdsim.vector_env import BatchedDeviceEnv, EnvConfig
+    from qdsim.virtualisation import make_capacitance_cnn
+    torch.manual_seed(0)
+    cnn = make_capacitance_cnn(3).cuda().eval()
+    for method in (None, "kalman"):
+        env = BatchedDeviceEnv(n_env3, 6, engine=eng, seed=1, capacitance_model=cnn if method else None,
+                               config=EnvConfig(resolution=64, max_steps=50, update_method=method, use_barriers=False,
+                                                algorithm="brute_force", max_charge_carriers=4))
+        if env.vg_updater is not None:
+            env.vg_updater.autocast_dtype = torch.bfloat16
+        env.reset()
+        rng = np.random.default_rng(0)
+        acts = [(rng.uniform(-0.1, 0.1, (n_env3, 6)), rng.uniform(-0.1, 0.1, (n_env3, 5))) for _ in range(4)]
+        env.step(*acts[0])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for a in acts[1:]:
+            env.step(*a)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / 3
+        c3[f"env_shell_brute_force_update_{method}"] = {"ms_per_step": dt * 1e3, "env_steps_per_s": n_env3 / dt,
+                                                         "pixels_per_s": n_env3 * 5 * 64 * 64 / dt}
     out[f"config3_6dot_{n_env3}env_64x64"] = c3
 
     # ---- config 5 ----
