@@ -575,6 +575,18 @@ def main():
             cpu = {"value": pps, "unit": "pixels/s", "cores": cores, "kind": "port",
                    "sample": f"{cpix // (res * res)} scans ({cpix} pixels) of the same workload, {cdt:.1f} s",
                    "what": kind}
+            # BASELINE.md section 3 variant 1, once: the literal NumPy restatement -- vectorised over the pixels of a scan,
+            # host Python loops for latching and telegraph noise exactly where the reference has them -- single process
+            from util import oracle_batch
+            n_lit = 6
+            t0 = time.perf_counter()
+            oracle_batch(mb, sets[0][:n_lit], flags)
+            dt_lit = time.perf_counter() - t0
+            cpu["variants"] = {"literal_numpy_single_process": {
+                "value": n_lit * res * res / dt_lit, "unit": "pixels/s", "cores": 1,
+                "sample": f"{n_lit} scans, {dt_lit:.1f} s",
+                "what": "oracle/scan.py: NumPy fp64 over the pixels of a scan, Python loops along the latching / telegraph "
+                        "chains (how the reference's host code is written)"}}
         out = {
             "metric": "ground_state_pixels_per_s", "value": value, "unit": "pixels/s",
             "env_steps_per_s": value / pix_per_env,

@@ -58,8 +58,13 @@ enum qd_ztype { QD_Z_F32 = 0, QD_Z_F16 = 1, QD_Z_U8 = 2 };
 #define QD_FLAG_RADIAL           0x04u  /* QADAPT radial noise / replacement (S7), per-scan rad_mode       */
 #define QD_FLAG_THERMAL          0x08u  /* honour per-env kT > 0 (Boltzmann average; non-integer charges)  */
 #define QD_FLAG_CARRY_ROWS       0x10u  /* latching + telegraph state carried across row ends (flat pass)  */
-#define QD_FLAG_LATCH_EXACT      0x20u  /* compare raw (not rounded) occupations when latching             */
+#define QD_FLAG_LATCH_EXACT      0x20u  /* compare raw (not rounded) occupations when latching: identical to the */
+                                        /* rounded compare on integer occupations; QD_ERR_UNSUPPORTED on         */
+                                        /* non-integer ones (QD_FLAG_THERMAL, QD_ALG_TUNNEL)                     */
 #define QD_FLAG_WHITE_ON_OUTPUT  0x40u  /* white noise added to the signal instead of the sensor occupation */
+#define QD_FLAG_PINK             0x80u  /* 1/f sensor input noise of amplitude pink_amp (north_star's "1-f noise"; the   */
+                                        /* reference itself has no 1/f model): sum of four Ornstein-        */
+                                        /* Uhlenbeck chains along the fast axis, correlation lengths 2, 8, 32, 128 pixels  */
 
 /* Per-env scalar parameters: the constructor arguments of ChargeSensedDotArray / TunnelCoupledChargeSensed,
  * LatchingModel, WhiteNoise, TelegraphNoise and BarrierVoltageModel (qarray_base_class.py:726-756, 779-838). */
@@ -78,7 +83,7 @@ typedef struct qd_env_params {
                                            /* 78-91, 128-141); 0, 0 = constant capacitances                  */
   int32_t max_charge_carriers;             /* brute_force                                                   */
   int32_t latching;                        /* 0: env has no LatchingModel                                   */
-  int32_t reserved[2];
+  double pink_amp;                         /* QD_FLAG_PINK: standard deviation of the 1/f input-noise term   */
 } qd_env_params;
 
 /* Shape and algorithm of a model set (all envs of one set share them). */

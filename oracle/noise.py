@@ -47,6 +47,45 @@ def input_noise(draws, ny, nx, white_amp, p01, p10, tele_amp, u_row, carry_rows=
     return z
 
 
+PINK_TAUS = (2.0, 8.0, 32.0, 128.0)
+
+
+def pink_noise(seed: int, ny: int, nx: int, carry_rows: bool = False):
+    """1/f sensor input noise, unit variance, shape (ny, nx) -- ``north_star`` names it; the reference has NO 1/f model
+    (SURVEY.md 8a S6), so this is the framework's own definition, restated here for the CUDA kernel to be checked against:
+
+    the sum of four Ornstein-Uhlenbeck chains along the fast axis, ``x_k[i] = a_k x_k[i-1] + sqrt(1 - a_k^2) xi_k[i]`` with
+    ``a_k = exp(-1 / tau_k)``, ``tau_k = 2, 8, 32, 128`` pixels (each of unit stationary variance; their sum / 2 has a spectrum
+    close to 1/f between 1/128 and 1/2 cycles per pixel).  ``xi_k[i]``: the four Box-Muller normals of Philox stream 2 at the
+    pixel; the state before the first pixel of a row (of the scan when ``carry_rows``): the same four normals of stream 3 at
+    the row index."""
+    from . import philox
+
+    def four_normals(index, purpose):
+        w0, w1, w2, w3 = philox.words(seed, index, purpose)
+        out = []
+        for wa, wb in ((w0, w1), (w2, w3)):
+            u1 = ((wa >> np.uint32(8)).astype(np.float64) + 1.0) * philox.INV_2_24
+            u2 = philox.u24(wb)
+            r = np.sqrt(-2.0 * np.log(u1))
+            out += [r * np.cos(2.0 * np.pi * u2), r * np.sin(2.0 * np.pi * u2)]
+        return np.stack(out, axis=-1)                      # (..., 4)
+
+    xi = four_normals(np.arange(ny * nx, dtype=np.uint64), 2).reshape(ny, nx, 4)
+    start = four_normals(np.arange(ny, dtype=np.uint64), 3)            # (ny, 4)
+    a = np.exp(-1.0 / np.asarray(PINK_TAUS))
+    b = np.sqrt(1.0 - a * a)
+    out = np.zeros((ny, nx))
+    x = start[0].copy()
+    for iy in range(ny):
+        if not carry_rows:
+            x = start[iy].copy()
+        for ix in range(nx):
+            x = a * x + b * xi[iy, ix]
+            out[iy, ix] = 0.5 * x.sum()
+    return out
+
+
 def radial_noise(z, z_radial, mode: int, x0, dx, y0, dy, alpha, zero_radius, max_amplitude):
     """``mode`` 0: off; 1: ``z + randn * clip(alpha*(dist - zero_radius), 0, max_amplitude)``; 2: ``randn`` replaces z.
 

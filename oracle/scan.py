@@ -33,6 +33,7 @@ class Model:
     tele_p01: float = 0.0
     tele_p10: float = 0.0
     tele_amp: float = 0.0
+    pink_amp: float = 0.0          # 1/f input noise (oracle/noise.py::pink_noise); 0 = off
     # Path B only
     n_gate: int = 0
     cbg: np.ndarray | None = None  # (B, G) raw positive
@@ -85,6 +86,8 @@ def simulate_points(m: Model, v, s: Scan, latch_compare: str = "rounded", carry_
                                   compare=latch_compare, carry_rows=carry_rows)
     noise_in = noise.input_noise(draws, ny, nx, m.white_amp, m.tele_p01, m.tele_p10, m.tele_amp, u_row,
                                  carry_rows=carry_rows, white_on=white_on)
+    if m.pink_amp != 0.0:
+        noise_in = noise_in + m.pink_amp * noise.pink_noise(s.seed, ny, nx, carry_rows=carry_rows)
     out_noise = None
     if white_on == "output" and m.white_amp != 0.0:
         out_noise = (m.white_amp * draws["z_white"]).reshape(ny * nx, 1)

@@ -58,9 +58,6 @@ struct qd_ctx {
   cudaStream_t last_stream = nullptr; //   for a launch on ANOTHER stream only once this has fired
   bool have_last = false;
   bool staged_pending = false;    // an asynchronous H2D out of h_scans may still be in flight
-  const void* configured[64] = {nullptr};   // kernels whose shared-memory attributes are already set ...
-  size_t configured_smem[64] = {0};         // ... and the dynamic size they were set for
-  int n_configured = 0;
   cudaEvent_t staged = nullptr;   // h_scans may be rewritten once this has fired
   cudaStream_t s_compute = nullptr, s_copy = nullptr;   // qd_scan_open_host: launches / result copies, overlapped
   cudaEvent_t chunk_done[16] = {nullptr};
@@ -163,7 +160,7 @@ kernel_fn pick_fast(int n) {
 // default / thresholded search with a hard argmin on affine windows runs the restructured kernel (qd_scan_fast_kernel);
 // QDSIM_GENERIC_SCAN=1 keeps the generic one (A/B timing, and the parity tests run both)
 bool use_fast_kernel(const qd_layout& L, unsigned flags, bool points) {
-  if (points || (flags & QD_FLAG_THERMAL)) return false;
+  if (points || (flags & (QD_FLAG_THERMAL | QD_FLAG_PINK))) return false;
   if (L.algorithm != QD_ALG_DEFAULT && L.algorithm != QD_ALG_THRESHOLDED) return false;
   const char* e = getenv("QDSIM_GENERIC_SCAN");
   return !(e && e[0] == '1');
@@ -215,18 +212,24 @@ int validate_launch(qd_ctx* ctx, int n_type, unsigned flags, const void* n_out) 
 }
 
 // shared-memory attributes of a kernel: set once per context (two driver calls saved per launch)
+// Function attributes belong to the CUDA context of a device, not to a qd_ctx: the table is process-wide, keyed by
+// (device, kernel), and the dynamic size only ever grows (two qd_ctx of one process must not lower each other's setting).
+struct KernelConfig { int device; const void* fn; size_t smem; };
+KernelConfig g_kernel_config[512];
+int g_n_kernel_config = 0;
+
 int configure_kernel(qd_ctx* ctx, const void* fn, size_t smem) {
   int at = -1;
-  for (int i = 0; i < ctx->n_configured; ++i)
-    if (ctx->configured[i] == fn) { at = i; break; }
-  if (at >= 0 && ctx->configured_smem[at] >= smem) return QD_OK;
-  if (smem > 48 * 1024 || at < 0)
-    QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+  for (int i = 0; i < g_n_kernel_config; ++i)
+    if (g_kernel_config[i].fn == fn && g_kernel_config[i].device == ctx->device) { at = i; break; }
+  if (at >= 0 && g_kernel_config[at].smem >= smem) return QD_OK;
+  const size_t want = std::max<size_t>(smem, 48 * 1024);
+  QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)want));
   // every warp stages its own record: ask for the largest shared-memory carveout so that registers, not shared
   // memory, bound the resident warps
   if (at < 0) QD_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  if (at < 0 && ctx->n_configured < 64) at = ctx->n_configured++;
-  if (at >= 0) { ctx->configured[at] = fn; ctx->configured_smem[at] = std::max<size_t>(smem, 48 * 1024); }
+  if (at < 0 && g_n_kernel_config < 512) at = g_n_kernel_config++;
+  if (at >= 0) g_kernel_config[at] = KernelConfig{ctx->device, fn, want};
   return QD_OK;
 }
 
@@ -382,7 +385,11 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   a.rows_per_item = (int)rows;
   a.items_per_scan = (max_ny + a.rows_per_item - 1) / a.rows_per_item;
   const long long total_items = (long long)n_scan * a.items_per_scan;
-  const int wpc = (total_items < (long long)ctx->sm_count * 4) ? 1 : QD_CTA_WARPS;
+  // warps per CTA: the warps of a CTA are independent, but a CTA's slot (registers, shared memory) is only released when
+  // its SLOWEST warp is done; scans differ in work (Gray-walk widths, latching events), so the restructured kernel runs
+  // one warp per CTA and lets the hardware scheduler balance (16 CTAs of 11.9 KB per SM).  QDSIM_WPC overrides (A/B).
+  int wpc = (total_items < (long long)ctx->sm_count * 4) ? 1 : (fast ? 1 : QD_CTA_WARPS);
+  if (const char* e = getenv("QDSIM_WPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) wpc = v; }
   long long grid = (total_items + wpc - 1) / wpc;
   if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
   const size_t smem = (size_t)a.slot_bytes * wpc;
@@ -705,6 +712,7 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
     par[QD_PAR_TC_BASE] = p.tc_base;
     par[QD_PAR_VC_ALPHA] = p.vc_alpha;
     par[QD_PAR_VC_BETA] = p.vc_beta;
+    par[QD_PAR_PINK] = p.pink_amp;
     for (int j = 0; j < 8; ++j) r[L.o_alpha + j] = p.alpha[j];
     for (int j = 0; j < 8; ++j) r[L.o_pleads + j] = p.p_leads[j];
     for (int j = 0; j < 64; ++j) r[L.o_pinter + j] = p.p_inter[j];
@@ -793,6 +801,7 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   int rc = validate_launch(ctx, n_type, flags, n_out_host);
   if (rc) return rc;
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  *ctx->h_status = 0u;      // report what THIS call's kernels raise (a caller of the async entries polls qd_status itself)
   int max_ny = 0;
   // one scan of a Path A model (a single do2d_open): the descriptor goes into the kernel parameters, no H2D copy
   const bool one = n_scan == 1 && scans && ctx->L.algorithm != QD_ALG_TUNNEL && scans[0].pix_offset == 0 &&
@@ -815,6 +824,7 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
   const long long pixels = ctx->up_pixels;
   const int N = ctx->L.n_dot;
   const size_t esz = n_elem_size(n_type);
+  const size_t zbytes = z_out_host ? (size_t)pixels * sizeof(float) : 0, nbytes = (size_t)pixels * N * esz;
   // ---- small calls (a single do2d_open): the kernel writes its outputs straight into mapped pinned host memory, so the
   // call is one descriptor copy, one launch (two on the tunnel path) and one synchronisation -- no device-to-host copies
   if (zbytes + nbytes <= (1u << 20) && n_scan <= 64) {
@@ -930,6 +940,7 @@ int qd_scan_obs_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, int scans_pe
     if (scans[i].nx != scans[0].nx || scans[i].ny != scans[0].ny || scans[i].pix_offset != (long long)i * per_scan)
       return fail(ctx, QD_ERR_INVALID, "scan %d: the observation path needs equal-size scans with pix_offset = i * nx * ny", i);
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  *ctx->h_status = 0u;
   int max_ny = 0;
   rc = stage_scans(ctx, n_scan, scans, ctx->s_compute, &max_ny, true);
   if (rc) return rc;
@@ -994,6 +1005,7 @@ int qd_points_open_host(qd_ctx* ctx, const qd_scan* scan, int ny, int nx, const 
   if (!scan || !v) return fail(ctx, QD_ERR_INVALID, "NULL argument to qd_points_open_host");
   if (nx <= 0 || ny <= 0) return fail(ctx, QD_ERR_INVALID, "nx, ny must be positive");
   QD_CUDA(ctx, cudaSetDevice(ctx->device));
+  *ctx->h_status = 0u;
   qd_scan s = *scan;
   s.nx = nx;
   s.ny = ny;

@@ -688,6 +688,8 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
   const bool f_thermal = a.flags & QD_FLAG_THERMAL;
   const bool f_carry = a.flags & QD_FLAG_CARRY_ROWS;
   const bool f_white_out = a.flags & QD_FLAG_WHITE_ON_OUTPUT;
+  const bool f_pink = a.flags & QD_FLAG_PINK;
+  double* d_pink = der + 40;    // state of the four 1/f chains at the last pixel processed (warp-uniform, in shared memory)
   const uint32_t rec_bytes = (uint32_t)L.rec_doubles * 8u;
 
   const long long total_items = (long long)a.n_scan * a.items_per_scan;
@@ -744,7 +746,9 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
           // tunnel path; the relaxed occupations never exceed max(g, 0) on an M-matrix).  uint8 charge maps and the
           // packed latching keys hold 0..255: flag windows that could leave that range instead of saturating silently.
           const double gmax = s0 + fmax(sx * (double)(sc->nx - 1), 0.0) + fmax(sy * (double)(sc->ny - 1), 0.0);
-          if (ALG != QD_ALG_BRUTE_FORCE && !(gmax < 252.0) && a.status) *reinterpret_cast<volatile unsigned*>(a.status) = QD_STATUS_OCC_OVERFLOW;
+          const bool replaced = (a.flags & QD_FLAG_RADIAL) && sc->rad_mode == 2;      // no occupations are computed there
+          if (ALG != QD_ALG_BRUTE_FORCE && !replaced && !(gmax < 252.0) && a.status)
+            *reinterpret_cast<volatile unsigned*>(a.status) = QD_STATUS_OCC_OVERFLOW;
         }
         else { d_us[0] = s0; d_us[1] = sx; d_us[2] = sy; }
       }
@@ -765,9 +769,10 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
     bool have_held = false;
     uint32_t tele_state = 0;
     bool tele_init = false;
+    bool pink_init = false;
 
     for (int iy = row0; iy < row1; ++iy) {
-      if (!f_carry) { have_held = false; tele_init = false; }
+      if (!f_carry) { have_held = false; tele_init = false; pink_init = false; }
       for (int c0 = 0; c0 < nx; c0 += 32) {
         const int ix = c0 + lane;
         const bool valid = ix < nx;
@@ -920,6 +925,55 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
               tele_state = __shfl_sync(0xffffffffu, st, 31);
               noise_in += tamp * (double)st;
             }
+          }
+          // ---- 1/f input noise: four Ornstein-Uhlenbeck chains x_k[i] = a_k x_k[i-1] + sqrt(1 - a_k^2) xi_k[i] along x,
+          // a_k = exp(-1 / tau_k), tau_k = 2, 8, 32, 128 pixels, unit stationary variance each; the term is
+          // pink_amp * (x_0 + x_1 + x_2 + x_3) / 2.  Draws: Philox purpose 2 (per pixel), 3 (stationary start of a row / of
+          // a flat pass).  A chain is a prefix scan of affine maps with a constant slope: five shuffle steps per chain.
+          if (f_pink && par[QD_PAR_PINK] != 0.0) {
+            if (!pink_init) {
+              const Philox4 ws = philox4x32_10(seed, (uint64_t)iy, 3u);
+              float s0, s1, s2, s3;
+              box_muller(ws.w0, ws.w1, s0, s1);
+              box_muller(ws.w2, ws.w3, s2, s3);
+              __syncwarp();
+              if (lane == 0) { d_pink[0] = (double)s0; d_pink[1] = (double)s1; d_pink[2] = (double)s2; d_pink[3] = (double)s3; }
+              __syncwarp();
+              pink_init = true;
+            }
+            const Philox4 wp = philox4x32_10(seed, (uint64_t)pix, 2u);
+            float e4[4];
+            box_muller(wp.w0, wp.w1, e4[0], e4[1]);
+            box_muller(wp.w2, wp.w3, e4[2], e4[3]);
+            const int last = 31 - __clz(vmask);
+            double psum = 0.0;
+            double xs_new[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const double ak = (k == 0) ? 0.60653065971263342 : (k == 1) ? 0.88249690258459546
+                              : (k == 2) ? 0.96923323447634413 : 0.99221793826024351;      // exp(-1/2), exp(-1/8), exp(-1/32), exp(-1/128)
+              double Bk = sqrt(1.0 - ak * ak) * (double)e4[k];
+              double ad = ak, apow = 1.0;
+#pragma unroll
+              for (int d = 1; d < 32; d <<= 1) {
+                const double tb = __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(Bk), d),
+                                                   __shfl_up_sync(0xffffffffu, __double2loint(Bk), d));
+                if (lane >= d) Bk = fma(ad, tb, Bk);
+                if ((lane + 1) & d) apow *= ad;
+                ad *= ad;
+              }
+              if ((lane + 1) & 32) apow *= ad;
+              const double xk = fma(apow, d_pink[k], Bk);
+              xs_new[k] = shfl_f64(xk, last);
+              psum += xk;
+            }
+            __syncwarp();
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) d_pink[k] = xs_new[k];
+            }
+            __syncwarp();
+            noise_in += par[QD_PAR_PINK] * 0.5 * psum;
           }
 
           // ---- sensor: ten Lorentzians of the first differences of the full-system free energy ----
@@ -1130,7 +1184,8 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_FAST_MIN_BLOCKS) qd_scan
         // occupations <= largest dot potential of the window + 1 (qd_scan_kernel has the argument): flag windows that
         // could leave the 0..255 range of the key bytes instead of saturating silently
         const double gmax = s0 + fmax(sx * (double)(nx - 1), 0.0) + fmax(sy * (double)(ny - 1), 0.0);
-        if (!(gmax < 252.0) && a.status) *reinterpret_cast<volatile unsigned*>(a.status) = QD_STATUS_OCC_OVERFLOW;
+        const bool replaced = (a.flags & QD_FLAG_RADIAL) && sc->rad_mode == 2;        // no occupations are computed there
+        if (!replaced && !(gmax < 252.0) && a.status) *reinterpret_cast<volatile unsigned*>(a.status) = QD_STATUS_OCC_OVERFLOW;
       } else { d_us[0] = s0; d_us[1] = sx; d_us[2] = sy; }
     }
     {

@@ -22,9 +22,10 @@ __device__ __forceinline__ float key_f32(uint32_t k) {
 }
 
 // numpy's _lerp (lib/_function_base_impl.py): a + (b-a) t, or b - (b-a)(1-t) when t >= 0.5
+// (explicitly rounded products and sums: an FMA contraction would differ from NumPy in the last bit)
 __device__ __forceinline__ double np_lerp(double a, double b, double t) {
-  const double d = b - a;
-  return (t >= 0.5) ? b - d * (1.0 - t) : a + d * t;
+  const double d = __dsub_rn(b, a);
+  return (t >= 0.5) ? __dsub_rn(b, __dmul_rn(d, __dsub_rn(1.0, t))) : __dadd_rn(a, __dmul_rn(d, t));
 }
 
 // typed store of a normalised value in [0, 1]: fp32, IEEE half, or uint8 = rint(255 v)

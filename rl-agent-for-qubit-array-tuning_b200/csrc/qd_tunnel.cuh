@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
 // =====================================================================================================================
 constexpr int QD_TS_SMALL = 16 + 8 + 8 + 8 + 8 + 16;     // vv[16] gs[8] ns[8] fs[8] hs[8] pad (select kernel)
 constexpr int QD_TS_WORK = QD_TS_SMALL + QD_T_TAB;
-constexpr int QD_TE_WORK = 32 * QD_T_HS + 6 * 32 + 96 + 32;   // H | dd ee e2 qi ll yy | vq | vv[16] gs[8] ts[8] (eigen kernel)
+constexpr int QD_TE_WORK = 32 * QD_T_HS + 6 * 32 + 72 + 32;   // H | dd ee e2 qi ll yy | vq | vv[16] gs[8] ts[8] (eigen kernel)
 
 __host__ __device__ inline int qd_tunnel_select_slot_bytes(const qd_layout& L) {
   return (L.gs_doubles * 8 + (int)sizeof(qd_scan) + QD_TS_WORK * 8 + 16 + 127) & ~127;
@@ -999,6 +999,29 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
                    (double)(((idx >> (2 * (NLO - 1 - j))) & 3) - 1);
         Ql[idx] = acc;
       }
+      if constexpr (NLO == 4) {
+        // Second-level bound (leading low digit fixed, the other three continuous): with the low block L = Cp_ll split as
+        // [[L00, l^T], [l, L']],  min_y' E = alpha + beta y0 + gamma y0^2,  gamma = L00 - l^T L'^-1 l  (per item),
+        // alpha = base - c'^T L'^-1 c',  beta = 2 (c0 - c'^T L'^-1 l)  (per block).  Stored: L'^-1 [9], L'^-1 l [3], gamma.
+        if (lane == 0) {
+          double Lm[4][4];
+          for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) Lm[i][j] = Cp[(NHI + i) * N + NHI + j];
+          const double a11 = Lm[1][1], a12 = Lm[1][2], a13 = Lm[1][3], a22 = Lm[2][2], a23 = Lm[2][3], a33 = Lm[3][3];
+          const double c11 = a22 * a33 - a23 * a23, c12 = a13 * a23 - a12 * a33, c13 = a12 * a23 - a13 * a22;
+          const double c22 = a11 * a33 - a13 * a13, c23 = a12 * a13 - a11 * a23, c33 = a11 * a22 - a12 * a12;
+          const double idet = 1.0 / (a11 * c11 + a12 * c12 + a13 * c13);
+          double* Mi = sv + 48;
+          Mi[0] = c11 * idet; Mi[1] = c12 * idet; Mi[2] = c13 * idet;
+          Mi[3] = c12 * idet; Mi[4] = c22 * idet; Mi[5] = c23 * idet;
+          Mi[6] = c13 * idet; Mi[7] = c23 * idet; Mi[8] = c33 * idet;
+          const double l1 = Lm[1][0], l2 = Lm[2][0], l3 = Lm[3][0];
+          Mi[9] = Mi[0] * l1 + Mi[1] * l2 + Mi[2] * l3;
+          Mi[10] = Mi[3] * l1 + Mi[4] * l2 + Mi[5] * l3;
+          Mi[11] = Mi[6] * l1 + Mi[7] * l2 + Mi[8] * l3;
+          Mi[12] = Lm[0][0] - (l1 * Mi[9] + l2 * Mi[10] + l3 * Mi[11]);
+        }
+      }
       __syncwarp();
     }
 
@@ -1119,19 +1142,34 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
         lb[i] = v;
       }
       while (true) {
-        double m = INF;
-        int mb = 0x7fffffff;
+        int mb;
+        if (have_prev) {
+          // Warm-started list: tau is (nearly) final from the start, so the ORDER of the visits hardly matters -- take any
+          // block whose bound is not above tau (one ballot instead of a 5-step (bound, index) reduction).  The set of
+          // candidates that end up in the list does not depend on the order; the walk ends when no such block is left.
+          int mine = -1;
 #pragma unroll
-        for (int i = 0; i < HI_IT; ++i)
-          if (lb[i] < m) { m = lb[i]; mb = i * 32 + lane; }
+          for (int i = HI_IT - 1; i >= 0; --i)
+            if (lb[i] - 1e-12 * (fabs(lb[i]) + 1.0) <= tau) mine = i * 32 + lane;       // (inf - inf = nan: not live)
+          const unsigned live = __ballot_sync(0xffffffffu, mine >= 0);
+          if (!live) break;
+          mb = __shfl_sync(0xffffffffu, mine, __ffs(live) - 1);
+        } else {
+          // cold start (first pixel of an item): best-first, so that tau tightens as early as possible
+          double m = INF;
+          mb = 0x7fffffff;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const double om = shfl_f64(m, lane ^ o);
-          const int ob = __shfl_xor_sync(0xffffffffu, mb, o);
-          if (om < m || (om == m && ob < mb)) { m = om; mb = ob; }
+          for (int i = 0; i < HI_IT; ++i)
+            if (lb[i] < m) { m = lb[i]; mb = i * 32 + lane; }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double om = shfl_f64(m, lane ^ o);
+            const int ob = __shfl_xor_sync(0xffffffffu, mb, o);
+            if (om < m || (om == m && ob < mb)) { m = om; mb = ob; }
+          }
+          if (!(m < INF)) break;
+          if (m - 1e-12 * (fabs(m) + 1.0) > tau) break;      // every remaining candidate is above the 32nd best
         }
-        if (!(m < INF)) break;
-        if (m - 1e-12 * (fabs(m) + 1.0) > tau) break;      // every remaining candidate is above the 32nd best
 #pragma unroll
         for (int i = 0; i < HI_IT; ++i)
           if (mb == i * 32 + lane) lb[i] = INF;
@@ -1139,9 +1177,26 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
         double c[NLO];
         tunnel_block_constants<N, NHI, NLO>(mb, E0, h, Cp, base, c);
         const double base_lane = tunnel_lane_part<NLO>(base, c, lane);      // lane part, once per block
+        double alpha_b = 0.0, beta_b = 0.0, gamma_b = 0.0;
+        if constexpr (NLO == 4) {
+          const double* __restrict__ Mi = sv + 48;
+          const double u0 = fma(Mi[0], c[1], fma(Mi[1], c[2], Mi[2] * c[3]));
+          const double u1 = fma(Mi[3], c[1], fma(Mi[4], c[2], Mi[5] * c[3]));
+          const double u2 = fma(Mi[6], c[1], fma(Mi[7], c[2], Mi[8] * c[3]));
+          alpha_b = base - fma(c[1], u0, fma(c[2], u1, c[3] * u2));
+          beta_b = 2.0 * (c[0] - fma(c[1], Mi[9], fma(c[2], Mi[10], c[3] * Mi[11])));
+          gamma_b = Mi[12];
+        }
 #pragma unroll 1
         for (int ii = 0; ii < LO_IT; ++ii) {
           const int i = (LO_IT >= 4) ? ((ii + LO_IT / 4) & (LO_IT - 1)) : ii;
+          if constexpr (NLO == 4) {
+            // every candidate of this iteration has the leading low digit i >> 1: skip it when even the continuous minimum
+            // over the other three low digits lies above the current 32nd-best energy
+            const double y0 = (double)((i >> 1) - 1);
+            const double bnd = fma(y0, fma(gamma_b, y0, beta_b), alpha_b);
+            if (bnd - 1e-12 * (fabs(bnd) + 1.0) > tau) continue;
+          }
           const int b = i * 32 + lane;
           const bool ok = (lo_valid >> i) & 1u;
           double e = INF;
@@ -1215,8 +1270,8 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
   double* qi = e2 + 32;
   double* ll = qi + 32;
   double* yy = ll + 32;
-  double* vq = yy + 32;          // interleaved (v_j, q_j) of the current Householder step, 64 doubles (+ one spare row)
-  double* vv = vq + 96;
+  double* vq = yy + 32;          // interleaved (v_j, q_j) of the current Householder step, 64 doubles (+ pad)
+  double* vv = vq + 72;
   double* gs = vv + 16;
   double* ts = gs + 8;
   uint64_t* bar = reinterpret_cast<uint64_t*>(wk + QD_TE_WORK);
@@ -1422,16 +1477,38 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
       if (lane == s1) ee[lane] = 0.0;
       else if (lane == s1 - 1) ee[lane] = H[s1 * QD_T_HS + lane];
       __syncwarp();
+      // Which sectors can hold the ground state at all?  lambda_min(sector) lies in [min_i (d_i - r_i), min_i d_i] (Gershgorin /
+      // Rayleigh quotients of the unit vectors, on the sector's own tridiagonal); a sector whose lower end exceeds the
+      // smallest diagonal entry U of the whole matrix is out.  The multisection then runs over the lane range that covers
+      // the candidate sectors only (the others inside that range have every eigenvalue above U: their minors stay positive).
       double lo, hi;
+      int c_lo, c_hi;
       {
         const double rad = ((lane > 0) ? fabs(ee[lane - 1]) : 0.0) + ((lane < 31) ? fabs(ee[lane]) : 0.0);
-        lo = warp_min(dd[lane] - rad);
-        hi = warp_max(dd[lane] + rad);
+        const double lower = dd[lane] - rad;
+        const double U = warp_min(dd[lane]);
+        double ls = lower;                                   // segmented minimum over the lane's own sector
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const double t = __hiloint2double(__shfl_up_sync(0xffffffffu, __double2hiint(ls), d),
+                                            __shfl_up_sync(0xffffffffu, __double2loint(ls), d));
+          if (lane - d >= s0) ls = fmin(ls, t);
+        }
+        ls = shfl_f64(ls, s1);
+        const bool cand = ls <= U;
+        const unsigned cm = __ballot_sync(0xffffffffu, cand);          // never empty: the sector that owns U is in
+        c_lo = __ffs(cm) - 1;
+        c_hi = 31 - __clz(cm);
+        lo = warp_min(cand ? lower : U);
+        hi = U;
+        const double wfull = warp_max(dd[lane] + rad) - warp_min(lower);
+        // bracket width for the scaling below: not narrower than 1e-3 of the full Gershgorin width, so that the scaled
+        // entries stay <= 1e3 in magnitude and the minors cannot overflow within a sector
+        hi = fmax(hi, lo + 1e-3 * wfull);
       }
       // Lowest eigenvalue by 32-way multisection.  x < lambda_0  <=>  T - x I positive definite  <=>  every leading
       // principal minor p_i(x) > 0 (Sylvester); the minors obey p_{i+1} = (d_i - x) p_i - e_{i-1}^2 p_{i-1}.  The
-      // tridiagonal is mapped onto [0, 1] first (Gershgorin interval), so |d - x| <= 1, e^2 <= 1 and the minors
-      // cannot overflow; a positive rescale every 8 steps guards the underflow side.
+      // tridiagonal is mapped onto the bracket [0, 1] first; a positive rescale every 8 steps guards the underflow side.
       const double lo0 = lo, wid = fmax(hi - lo, 1e-300), iw = 1.0 / wid;
       qi[lane] = (dd[lane] - lo0) * iw;
       e2[lane] = (ee[lane] * iw) * (ee[lane] * iw);
@@ -1440,18 +1517,22 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
       hi = 1.0;
       for (int round = 0; round < 6; ++round) {
         const double x = fma((double)(lane + 1) * (1.0 / 33.0), hi - lo, lo);
-        double pp = 1.0, pc = qi[0] - x;
+        double pp = 1.0, pc = qi[c_lo] - x;
         bool below = !(pc > 0.0);                  // some eigenvalue lies at or below x
-#pragma unroll
-        for (int i0 = 1; i0 < 32; i0 += 8) {
-#pragma unroll
-          for (int i = i0; i < i0 + 8 && i < 32; ++i) {
+        int i = c_lo + 1;
+#pragma unroll 1
+        while (i <= c_hi) {
+          const int i1 = min(i + 8, c_hi + 1);
+#pragma unroll 1
+          for (; i < i1; ++i) {
             const double pn = fma(qi[i] - x, pc, -e2[i - 1] * pp);
             below |= !(pn > 0.0);
             pp = pc;
             pc = pn;
           }
-          if (pc < 1e-150) { pc *= 1e150; pp *= 1e150; }      // (irrelevant once `below` is set)
+          const double ap = fabs(pc);
+          if (ap < 1e-150) { pc *= 1e150; pp *= 1e150; }      // (irrelevant once `below` is set)
+          else if (ap > 1e150) { pc *= 1e-150; pp *= 1e-150; }
         }
         const unsigned mm = __ballot_sync(0xffffffffu, below);
         const int j = mm ? __ffs(mm) - 1 : 32;

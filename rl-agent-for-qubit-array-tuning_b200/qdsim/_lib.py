@@ -23,7 +23,7 @@ Z_DTYPES = {Z_F32: np.float32, Z_F16: np.float16, Z_U8: np.uint8}
 STATUS_OCC_OVERFLOW = 0x1
 # flags
 FLAG_LATCH, FLAG_NOISE, FLAG_RADIAL, FLAG_THERMAL = 0x01, 0x02, 0x04, 0x08
-FLAG_CARRY_ROWS, FLAG_LATCH_EXACT, FLAG_WHITE_ON_OUTPUT = 0x10, 0x20, 0x40
+FLAG_CARRY_ROWS, FLAG_LATCH_EXACT, FLAG_WHITE_ON_OUTPUT, FLAG_PINK = 0x10, 0x20, 0x40, 0x80
 
 SCAN_DTYPE = np.dtype([
     ("v0", "f8", (QD_MAX_VOLT,)), ("dx", "f8", (QD_MAX_VOLT,)), ("dy", "f8", (QD_MAX_VOLT,)),
@@ -40,7 +40,7 @@ PARAMS_DTYPE = np.dtype([
     ("tele_p01", "f8"), ("tele_p10", "f8"), ("tele_amp", "f8"),
     ("p_leads", "f8", (QD_MAX_DOTS,)), ("p_inter", "f8", (QD_MAX_DOTS * QD_MAX_DOTS,)),
     ("tc_base", "f8"), ("alpha", "f8", (QD_MAX_DOTS,)), ("vc_alpha", "f8"), ("vc_beta", "f8"),
-    ("max_charge_carriers", "i4"), ("latching", "i4"), ("reserved", "i4", (2,)),
+    ("max_charge_carriers", "i4"), ("latching", "i4"), ("pink_amp", "f8"),
 ], align=True)
 assert PARAMS_DTYPE.itemsize == 728, PARAMS_DTYPE.itemsize
 

@@ -11,7 +11,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import _lib, maxwell
-from ._lib import (ALGORITHMS, FLAG_CARRY_ROWS, FLAG_LATCH, FLAG_LATCH_EXACT, FLAG_NOISE, FLAG_RADIAL,  # noqa: F401
+from ._lib import (ALGORITHMS, FLAG_CARRY_ROWS, FLAG_LATCH, FLAG_LATCH_EXACT, FLAG_NOISE, FLAG_PINK, FLAG_RADIAL,  # noqa: F401
                    FLAG_THERMAL, FLAG_WHITE_ON_OUTPUT, N_DTYPES, N_F32, N_F64, N_NONE, N_U8, PARAMS_DTYPE,
                    QD_MAX_DOTS, QD_MAX_VOLT, SCAN_DTYPE, Z_DTYPES, Z_F16, Z_F32, Z_U8, QdError)
 

@@ -246,3 +246,23 @@ def test_fast_kernel_flat_pass_and_wide_search(engine, monkeypatch):
     safe = (margin > 1e-9).all(axis=2)
     nf = res["0"][1][1].reshape(n_ref.shape)
     assert (nf.astype(np.int64) == np.rint(n_ref).astype(np.int64))[safe].all()
+
+
+@pytest.mark.parametrize("n_dot,res,carry", [(4, 40, False), (3, 33, True), (8, 64, False)])
+def test_pink_noise_matches_the_oracle_definition(engine, n_dot, res, carry):
+    """QD_FLAG_PINK (north_star's 1/f noise; the reference has none): draw-for-draw against oracle/noise.py::pink_noise."""
+    from qdsim import FLAG_CARRY_ROWS, FLAG_LATCH, FLAG_NOISE, FLAG_PINK, N_U8, synth
+    dev = synth.sample_devices(3, n_dot, seed=300 + n_dot)
+    mb = synth.model_batch(dev)
+    mb.params["pink_amp"] = [2e-3, 0.0, 5e-4]
+    engine.set_models(mb)
+    scans = synth.env_step_scans(mb, dev, res=res, seed=301, offset_range=2.0, radial=False)
+    flags = FLAG_LATCH | FLAG_NOISE | FLAG_PINK | (FLAG_CARRY_ROWS if carry else 0)
+    z, n = engine.scan_open_host(scans, n_type=N_U8, flags=flags)
+    z0, n0 = engine.scan_open_host(scans, n_type=N_U8, flags=flags & ~FLAG_PINK)
+    z_ref, n_ref, margin = oracle_batch(mb, scans, flags)
+    np.testing.assert_allclose(z.reshape(z_ref.shape), z_ref, rtol=0, atol=5e-6)
+    assert np.array_equal(n, n0)                                        # input noise does not touch the charge state
+    per_env = (n_dot - 1) * res * res
+    assert np.array_equal(z[per_env:2 * per_env], z0[per_env:2 * per_env])    # pink_amp = 0: term off
+    assert np.abs(z[:per_env] - z0[:per_env]).max() > 1e-4               # and it is really there for env 0

@@ -251,3 +251,19 @@ def test_whole_scan_oracle_runs_and_is_deterministic():
     s.seed = 78
     z3, _ = oscan.simulate_scan(m, s)
     assert not np.array_equal(z1, z3)
+
+
+def test_pink_noise_statistics_and_spectrum():
+    """The framework's own 1/f term (oracle/noise.py::pink_noise): unit-variance chains, spectrum ~ 1/f over two decades."""
+    from oracle import noise
+    x = noise.pink_noise(seed=12345, ny=64, nx=2048)
+    assert abs(x.mean()) < 0.05 and 0.8 < x.var() < 1.2
+    spec = (np.abs(np.fft.rfft(x, axis=1)) ** 2).mean(axis=0)
+    f = np.fft.rfftfreq(2048)
+    band = (f > 1 / 100) & (f < 1 / 6)
+    slope = np.polyfit(np.log(f[band]), np.log(spec[band]), 1)[0]
+    assert -1.35 < slope < -0.65, slope                      # 1/f within the band the four octaves cover
+    # rows are independent chains unless carried
+    y = noise.pink_noise(seed=12345, ny=4, nx=256, carry_rows=True)
+    z = noise.pink_noise(seed=12345, ny=4, nx=256, carry_rows=False)
+    assert np.array_equal(y[0], z[0]) and not np.allclose(y[1], z[1])

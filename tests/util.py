@@ -8,7 +8,7 @@ from oracle import scan as oscan
 
 
 def oracle_model(mb, e: int, flags: int = 0):
-    from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_THERMAL
+    from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_PINK, FLAG_THERMAL
     p = mb.params[e]
     n = mb.n_dot
     noise = bool(flags & FLAG_NOISE)
@@ -21,6 +21,7 @@ def oracle_model(mb, e: int, flags: int = 0):
         p_leads=p["p_leads"][:n].copy(), p_inter=p["p_inter"].reshape(8, 8)[:n, :n].copy(),
         white_amp=float(p["white_amp"]) if noise else 0.0, tele_p01=float(p["tele_p01"]),
         tele_p10=float(p["tele_p10"]), tele_amp=float(p["tele_amp"]) if noise else 0.0,
+        pink_amp=float(p["pink_amp"]) if (flags & FLAG_PINK) and "pink_amp" in (p.dtype.names or ()) else 0.0,
         n_gate=mb.n_gate, cbg=None if mb.cbg is None else mb.cbg[e], tc_base=float(p["tc_base"]),
         alpha=p["alpha"].copy(), num_charge_states=mb.num_charge_states,
         charge_state_batch_size=mb.charge_state_batch_size, vc_alpha=float(p["vc_alpha"]), vc_beta=float(p["vc_beta"]))
@@ -75,7 +76,7 @@ def _params_from_bytes(raw):
     if raw.size % PARAMS_DTYPE.itemsize == 0:
         return raw.view(PARAMS_DTYPE).copy()
     legacy = np.dtype([(n, PARAMS_DTYPE.fields[n][0]) for n in PARAMS_DTYPE.names if n not in ("vc_alpha", "vc_beta")],
-                      align=True)
+                      align=True)                      # (the trailing 8 bytes were `reserved`, now `pink_amp`: zero either way)
     assert legacy.itemsize == 712 and raw.size % 712 == 0, (legacy.itemsize, raw.size)
     old = raw.view(legacy)
     out = np.zeros(old.shape, dtype=PARAMS_DTYPE)
