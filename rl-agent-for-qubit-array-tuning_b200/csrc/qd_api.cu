@@ -272,6 +272,8 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
     g.L = ctx->L; g.records = ctx->d_records; g.scans = d_scans; g.points = d_points; g.z_out = nullptr;
     g.n_out = nullptr; g.nbar = ctx->d_nbar; g.n_scan = n_scan; g.n_type = QD_N_NONE; g.flags = flags;
     g.status = ctx->d_status;
+    g.topt = 7;
+    if (const char* e = getenv("QDSIM_TUNNEL_OPT")) g.topt = atoi(e);
     const long long max_pix = ctx->up_max_pix;
     const char* mono_e = getenv("QDSIM_TUNNEL_MONO");
     const bool mono = mono_e && mono_e[0] == '1';
@@ -726,24 +728,6 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
       r[L.o_spos + j] = sp;
       r[L.o_sneg + j] = sn;
     }
-    if (alg == QD_ALG_BRUTE_FORCE) {
-      // cdd_inv = U D U^T, U unit upper triangular (the branch-and-bound order of ground_state_brute: dot 0 outermost)
-      double* d = r + L.o_ud;
-      double* U = r + L.o_ud + 8;
-      const double* Cm = r + L.o_cinv;
-      for (int k = N - 1; k >= 0; --k) {
-        double dk = Cm[k * N + k];
-        for (int j = k + 1; j < N; ++j) dk -= U[k * N + j] * U[k * N + j] * d[j];
-        if (!(dk > 0.0)) return fail(ctx, QD_ERR_INVALID, "env %d: cdd_inv is not positive definite", e);
-        d[k] = dk;
-        U[k * N + k] = 1.0;
-        for (int i = 0; i < k; ++i) {
-          double u = Cm[i * N + k];
-          for (int j = k + 1; j < N; ++j) u -= U[i * N + j] * U[k * N + j] * d[j];
-          U[i * N + k] = u / dk;
-        }
-      }
-    }
     if (alg == QD_ALG_TUNNEL) {
       if (cbg && NV > G) memcpy(r + L.o_cbg, cbg + (size_t)e * (NV - G) * G, sizeof(double) * (NV - G) * G);
     }
@@ -894,7 +878,9 @@ template <typename OUT>
 int normalise_launch(qd_ctx* ctx, const float* z, OUT* out, int64_t per_env, int n_env, double ql, double qh, double* stats,
                      cudaStream_t stream) {
   const size_t need = (size_t)per_env * sizeof(float);
-  if (need <= 200 * 1024) {          // the env's image fits in shared memory: one HBM read per pixel
+  if (per_env <= 32 * 1024) {        // the env's image fits in the registers of one CTA: one HBM read per pixel
+    qd::qd_normalise_reg_kernel<OUT><<<n_env, 1024, 0, stream>>>(z, out, per_env, n_env, ql, qh, stats);
+  } else if (need <= 200 * 1024) {   // ... or in its shared memory
     auto fn = qd::qd_normalise_kernel<OUT, true>;
     if (need > 40 * 1024) {
       int rc = configure_kernel(ctx, (const void*)fn, need);

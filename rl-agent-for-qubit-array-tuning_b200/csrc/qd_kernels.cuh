@@ -41,6 +41,7 @@ struct KArgs {
   unsigned char* tfloor;               // [slots][8]   floor of the relaxed continuous occupations
   unsigned long long* tkeys;           // [slots][32]  the 32 kept basis states, 8 bits per dot
   long long tstride;                   // pixels per scan slot (largest scan of the upload)
+  int topt;                            // tunnel path: optimisation switches (QDSIM_TUNNEL_OPT, default all on; A/B and bisection)
   // single-scan fast path (one do2d_open): the descriptor travels in the kernel parameters instead of through a
   // host-to-device copy; `scans` is then unused
   int use_one;
@@ -56,9 +57,12 @@ struct KArgs {
 constexpr int QD_DER_DOUBLES = 48;  // derived per-item block: g0[8] gx[8] gy[8] us0 usx usy pad[5] carry[8] + spare
 constexpr int QD_PC_DOUBLES = 8 * 64 + 8 * 16 + 8 + 8 * 32 + 8 * 24;   // projection cache: 8 matrices, inversion scratch, keys + meta; per-lane lin[8]; affine forms
 
+constexpr int QD_BF_DOUBLES = 8 + 64 + 8;   // brute force, per item: d[8], U[64] of the PERMUTED cdd_inv, perm / inverse perm (16 ints)
+
 __host__ __device__ inline int qd_slot_bytes(const qd_layout& L) {
   int b = L.rec_doubles * 8 + (int)sizeof(qd_scan) + QD_DER_DOUBLES * 8 + 16;
   if (L.algorithm == QD_ALG_DEFAULT || L.algorithm == QD_ALG_THRESHOLDED) b += QD_PC_DOUBLES * 8;
+  if (L.algorithm == QD_ALG_BRUTE_FORCE) b += QD_BF_DOUBLES * 8;
   return (b + 127) & ~127;
 }
 
@@ -582,10 +586,17 @@ struct BruteLevel<N, N> {
                                              double&, unsigned&, double, double, double&, double (&)[N]) {}
 };
 
+// `ud`: d[8] | U[64] of cdd_inv with rows / columns permuted by `pm` (pm[l] = dot at tree level l, pm[8 + j] = level of dot
+// j); `gp`: the potentials in that order.  The order is chosen per work item (most negative potential first): a dot far below
+// its first transition is pinned to 0 carriers, and with it at the TOP of the tree its unavoidable cost sits in every
+// partial sum and conditions the centres of the levels below -- the bound bites.  (With such dots at the bottom the
+// unconstrained completion the bound assumes is far below anything the box allows, and the walk degenerates.)
+// Exact energy ties (measure zero; the parity tests skip margins <= 1e-9) resolve in tree order.
 template <int N, bool THERMAL>
-__device__ __forceinline__ void ground_state_brute(const double (&g)[N], const double* __restrict__ rec,
-                                                   const qd_layout& L, double kT, double (&nd)[N]) {
-  const double* __restrict__ ud = rec + L.o_ud;
+__device__ __forceinline__ void ground_state_brute(const double (&gp)[N], const double* __restrict__ rec,
+                                                   const qd_layout& L, const double* __restrict__ ud,
+                                                   const int* __restrict__ pm, double kT, double (&nd)[N]) {
+  const double (&g)[N] = gp;
   const int maxc = (int)rec[L.o_par + QD_PAR_MAXC];
   double Z = 0.0;
   double s[N], acc[N];
@@ -617,11 +628,21 @@ __device__ __forceinline__ void ground_state_brute(const double (&g)[N], const d
     unsigned dummy = 0;
     BruteLevel<N, 0>::template run<1>(ud, g, maxc, 0.0, s, 0u, cut, dummy, best, 1.0 / kT, Z, acc);
     const double invZ = 1.0 / Z;
+    double np_[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j) nd[j] = acc[j] * invZ;
+    for (int l = 0; l < N; ++l) np_[l] = acc[l] * invZ;
+    // level l -> dot pm[l]
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const int lv = pm[8 + j];
+      double v = np_[0];
+#pragma unroll
+      for (int l = 1; l < N; ++l) v = (lv == l) ? np_[l] : v;
+      nd[j] = v;
+    }
   } else {
 #pragma unroll
-    for (int j = 0; j < N; ++j) nd[j] = (double)((bcode >> (4 * (N - 1 - j))) & 15u);
+    for (int j = 0; j < N; ++j) nd[j] = (double)((bcode >> (4 * (N - 1 - pm[8 + j]))) & 15u);
   }
 }
 
@@ -669,6 +690,8 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
   double* d_us = der + 24;      // us0, usx, usy
   double* d_carry = der + 32;   // latched configuration of the last pixel of the previous chunk
   ProjCache pc;
+  double* bf_ud = reinterpret_cast<double*>(bar + 2);            // brute force: per-item factor of the permuted cdd_inv
+  int* bf_pm = reinterpret_cast<int*>(bf_ud + 72);
   pc.mats = reinterpret_cast<double*>(bar + 2);
   pc.aug = pc.mats + 8 * 64;
   pc.keys = reinterpret_cast<uint32_t*>(pc.aug + 8 * 16);
@@ -754,6 +777,42 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
       }
     }
     __syncwarp();
+    if constexpr (ALG == QD_ALG_BRUTE_FORCE) {
+      // ---- tree order of this item (most negative potential at the item's centre first) and cdd_inv = U D U^T in it ----
+      if (lane == 0) {
+        int ord[N];
+        double gc[N];
+        for (int j = 0; j < N; ++j) {
+          ord[j] = j;
+          gc[j] = POINTS ? 0.0 : fma(0.5 * (double)(row0 + row1 - 1), d_gy[j], fma(0.5 * (double)(nx - 1), d_gx[j], d_g0[j]));
+        }
+        if (!POINTS) {
+          for (int i = 1; i < N; ++i) {                    // insertion sort by potential, ascending
+            const int o = ord[i];
+            int j = i - 1;
+            while (j >= 0 && gc[ord[j]] > gc[o]) { ord[j + 1] = ord[j]; --j; }
+            ord[j + 1] = o;
+          }
+        }
+        for (int l = 0; l < N; ++l) { bf_pm[l] = ord[l]; bf_pm[8 + ord[l]] = l; }
+        const double* __restrict__ Cm = rec + L.o_cinv;
+        double* d = bf_ud;
+        double* U = bf_ud + 8;
+        for (int k = N - 1; k >= 0; --k) {
+          double dk = Cm[ord[k] * N + ord[k]];
+          for (int j = k + 1; j < N; ++j) dk -= U[k * N + j] * U[k * N + j] * d[j];
+          d[k] = dk;
+          U[k * N + k] = 1.0;
+          const double idk = 1.0 / dk;
+          for (int i = 0; i < k; ++i) {
+            double u = Cm[ord[i] * N + ord[k]];
+            for (int j = k + 1; j < N; ++j) u -= U[i * N + j] * U[k * N + j] * d[j];
+            U[i * N + k] = u * idk;
+          }
+        }
+      }
+      __syncwarp();
+    }
 
     const double* par = rec + L.o_par;
     const double kT = (THERMAL && f_thermal) ? par[QD_PAR_KT] : 0.0;
@@ -825,7 +884,18 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
             const double* __restrict__ src = a.nbar + (size_t)(pix0 + pix) * N;
 #pragma unroll
             for (int j = 0; j < N; ++j) nd[j] = src[j];
-          } else if constexpr (ALG == QD_ALG_BRUTE_FORCE) ground_state_brute<N, THERMAL>(g, rec, L, kT, nd);
+          } else if constexpr (ALG == QD_ALG_BRUTE_FORCE) {
+            double gp[N];                            // potentials in tree order
+            if constexpr (!POINTS) {
+              const double fx = (double)ixc, fy = (double)iy;
+#pragma unroll
+              for (int l = 0; l < N; ++l) { const int j = bf_pm[l]; gp[l] = fma(fy, d_gy[j], fma(fx, d_gx[j], d_g0[j])); }
+            } else {
+#pragma unroll
+              for (int l = 0; l < N; ++l) gp[l] = g[l];           // explicit voltage lists keep the identity order
+            }
+            ground_state_brute<N, THERMAL>(gp, rec, L, bf_ud, bf_pm, kT, nd);
+          }
           else ground_state_box<N, THERMAL, !POINTS>(g, rec, L, pc, lane, L.algorithm == QD_ALG_THRESHOLDED, kT, (double)ixc, (double)iy, nd);
 
           // ---- hysteresis latching along x ----

@@ -41,8 +41,7 @@ struct qd_layout {
   int32_t o_q;       // [2^N]      Q[delta] = delta^T cdd_inv delta, delta in {0,1}^N, dot 0 = most significant bit
   int32_t o_cbg;     // [B*G]      (tunnel) raw positive barrier-gate matrix
   int32_t gs_doubles;   // (tunnel) length of the record PREFIX the ground-state kernel stages: cinv | a | par | alpha | cbg
-  int32_t o_ud;      // [8 + N*N]  (brute force) cdd_inv = U D U^T: d[8], then unit upper triangular U row-major (branch and bound)
-  int32_t pad1;
+  int32_t pad0, pad1;
   int32_t rec_doubles;  // total, multiple of 2 (16 bytes)
 };
 
@@ -89,9 +88,7 @@ static inline qd_layout qd_make_layout(int n_dot, int n_volt, int n_gate, int al
     L.o_cbg = o;
     L.gs_doubles = 0;
   }
-  L.o_ud = o;
-  if (algorithm == QD_ALG_BRUTE_FORCE) o += 8 + n_dot * n_dot;
-  L.pad1 = 0;
+  L.pad0 = L.pad1 = 0;
   // (the tunnel path's block tables depend on a per-item permutation of the dots and are built inside the kernel)
   L.rec_doubles = (o + 1) & ~1;
   return L;

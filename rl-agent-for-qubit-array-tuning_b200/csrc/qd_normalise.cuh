@@ -33,13 +33,126 @@ __device__ __forceinline__ void store_norm(float* p, double v) { *p = (float)v; 
 __device__ __forceinline__ void store_norm(__half* p, double v) { *p = __float2half_rn((float)v); }
 __device__ __forceinline__ void store_norm(unsigned char* p, double v) { *p = (unsigned char)__double2int_rn(255.0 * v); }
 
-// One histogram update per distinct bin of the warp instead of one shared-memory atomic per lane: the top bytes of a
-// sensor image fall into two or three bins, where 32 same-address atomics would serialise.
+// Histogram update of one warp: when every participating lane hits the same bin (a plateau of the image -- the common
+// case in the leading digits) one lane adds the count; otherwise plain shared-memory atomics.
 __device__ __forceinline__ void hist_add(unsigned* hist, uint32_t b, bool on) {
   const unsigned act = __ballot_sync(0xffffffffu, on);
-  if (!on) return;
-  const unsigned peers = __match_any_sync(act, b);
-  if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[b], (unsigned)__popc(peers));
+  if (!act) return;
+  const uint32_t b0 = __shfl_sync(0xffffffffu, b, __ffs(act) - 1);
+  if (__all_sync(0xffffffffu, !on || b == b0)) {
+    if ((int)(threadIdx.x & 31) == __ffs(act) - 1) atomicAdd(&hist[b0], (unsigned)__popc(act));
+  } else if (on) {
+    atomicAdd(&hist[b], 1u);
+  }
+}
+
+// The production kernel: one CTA of 1024 threads per env, the env's image held in REGISTERS (up to 32 values per thread,
+// i.e. 32768 pixels per env: 8 dots x 64 x 64 = 28672), so HBM sees one 4-byte read and one typed write per pixel and the
+// radix passes touch no memory but their histograms.  Passes whose byte is the same for every pixel of the env (sign and
+// exponent of a sensor image, mostly) are skipped outright: (kmin >> shift) == (kmax >> shift).
+template <typename OUT>
+__global__ void __launch_bounds__(1024) qd_normalise_reg_kernel(const float* __restrict__ z, OUT* __restrict__ out,
+                                                                long long per_env, int n_env, double q_lo, double q_hi,
+                                                                double* __restrict__ stats) {
+  constexpr int EPT = 32;
+  __shared__ unsigned hist[4][256];
+  __shared__ uint32_t prefix[4];
+  __shared__ long long rank[4];
+  __shared__ uint32_t red[2][32];
+  const int env = blockIdx.x;
+  if (env >= n_env) return;
+  const float* __restrict__ src = z + (size_t)env * per_env;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  uint32_t key[EPT];
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const long long i = (long long)e * 1024 + tid;
+    key[e] = 0u;
+    if (i < per_env) {
+      key[e] = f32_key(src[i]);
+      kmin = min(kmin, key[e]);
+      kmax = max(kmax, key[e]);
+    }
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) { red[0][wid] = kmin; red[1][wid] = kmax; }
+  // (explicitly rounded product: contracted into the subtraction below it would differ from NumPy in the last bit of t)
+  const double vi_lo = __dmul_rn((double)(per_env - 1), q_lo), vi_hi = __dmul_rn((double)(per_env - 1), q_hi);
+  const long long k_lo = (long long)floor(vi_lo), k_hi = (long long)floor(vi_hi);
+  if (tid == 0) {
+    rank[0] = k_lo; rank[1] = min(k_lo + 1, per_env - 1);
+    rank[2] = k_hi; rank[3] = min(k_hi + 1, per_env - 1);
+    prefix[0] = prefix[1] = prefix[2] = prefix[3] = 0u;
+  }
+  __syncthreads();
+  kmin = __reduce_min_sync(0xffffffffu, red[0][lane]);
+  kmax = __reduce_max_sync(0xffffffffu, red[1][lane]);
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    if ((kmin >> shift) == (kmax >> shift)) {          // every pixel shares this byte (and all above): nothing to select
+      __syncthreads();
+      if (tid < 4) prefix[tid] |= ((kmin >> shift) & 0xffu) << shift;
+      __syncthreads();
+      continue;
+    }
+    for (int i = tid; i < 4 * 256; i += 1024) (&hist[0][0])[i] = 0u;
+    __syncthreads();
+    const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
+    const uint32_t p0 = prefix[0], p1 = prefix[1], p2 = prefix[2], p3 = prefix[3];
+    const bool d1 = p1 != p0, d2 = p2 != p0 && p2 != p1, d3 = p3 != p0 && p3 != p1 && p3 != p2;
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+      const long long i = (long long)e * 1024 + tid;
+      if ((long long)e * 1024 >= per_env) break;       // (uniform over the CTA)
+      const bool in = i < per_env;
+      const uint32_t k = key[e];
+      const uint32_t b = (k >> shift) & 0xffu, top = k & hi_mask;
+      hist_add(hist[0], b, in && top == p0);
+      if (d1) hist_add(hist[1], b, in && top == p1);
+      if (d2) hist_add(hist[2], b, in && top == p2);
+      if (d3) hist_add(hist[3], b, in && top == p3);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      const int b = tid;
+      if (!d1) hist[1][b] = hist[0][b];
+      if (!d2) hist[2][b] = (p2 == p0) ? hist[0][b] : hist[1][b];
+      if (!d3) hist[3][b] = (p3 == p0) ? hist[0][b] : (p3 == p1) ? hist[1][b] : hist[2][b];
+    }
+    __syncthreads();
+    if (tid < 4) {
+      const int t = tid;
+      long long r = rank[t];
+      int b = 0;
+      for (; b < 255; ++b) {
+        const unsigned c = hist[t][b];
+        if (r < (long long)c) break;
+        r -= c;
+      }
+      rank[t] = r;
+      prefix[t] |= (uint32_t)b << shift;
+    }
+    __syncthreads();
+  }
+  const double a_lo = (double)key_f32(prefix[0]), b_lo = (double)key_f32(prefix[1]);
+  const double a_hi = (double)key_f32(prefix[2]), b_hi = (double)key_f32(prefix[3]);
+  const double p_low = np_lerp(a_lo, b_lo, __dsub_rn(vi_lo, (double)k_lo));
+  const double p_high = np_lerp(a_hi, b_hi, __dsub_rn(vi_hi, (double)k_hi));
+  if (stats && tid == 0) { stats[2 * env] = p_low; stats[2 * env + 1] = p_high; }
+  const bool ok = p_high > p_low;
+  const double span = p_high - p_low;
+  OUT* __restrict__ dst = out + (size_t)env * per_env;
+#pragma unroll
+  for (int e = 0; e < EPT; ++e) {
+    const long long i = (long long)e * 1024 + tid;
+    if (i < per_env) {
+      double v = ok ? ((double)key_f32(key[e]) - p_low) / span : 0.0;
+      v = fmin(fmax(v, 0.0), 1.0);
+      store_norm(dst + i, v);
+    }
+  }
 }
 
 // RESIDENT = true: the env's image is staged in shared memory once (dynamic smem of per_env floats) and the four radix
@@ -62,7 +175,8 @@ __global__ void __launch_bounds__(1024) qd_normalise_kernel(const float* __restr
   }
   const float* __restrict__ src = RESIDENT ? zs : gsrc;
   // numpy 'linear' percentile: virtual index (n-1) q, neighbours floor / floor+1 (clamped), weight = fractional part
-  const double vi_lo = (double)(per_env - 1) * q_lo, vi_hi = (double)(per_env - 1) * q_hi;
+  // (explicitly rounded product: contracted into the subtraction below it would differ from NumPy in the last bit of t)
+  const double vi_lo = __dmul_rn((double)(per_env - 1), q_lo), vi_hi = __dmul_rn((double)(per_env - 1), q_hi);
   const long long k_lo = (long long)floor(vi_lo), k_hi = (long long)floor(vi_hi);
   if (threadIdx.x == 0) {
     rank[0] = k_lo; rank[1] = min(k_lo + 1, per_env - 1);
@@ -112,8 +226,8 @@ __global__ void __launch_bounds__(1024) qd_normalise_kernel(const float* __restr
   }
   const double a_lo = (double)key_f32(prefix[0]), b_lo = (double)key_f32(prefix[1]);
   const double a_hi = (double)key_f32(prefix[2]), b_hi = (double)key_f32(prefix[3]);
-  const double p_low = np_lerp(a_lo, b_lo, vi_lo - (double)k_lo);
-  const double p_high = np_lerp(a_hi, b_hi, vi_hi - (double)k_hi);
+  const double p_low = np_lerp(a_lo, b_lo, __dsub_rn(vi_lo, (double)k_lo));
+  const double p_high = np_lerp(a_hi, b_hi, __dsub_rn(vi_hi, (double)k_hi));
   if (stats && threadIdx.x == 0) { stats[2 * env] = p_low; stats[2 * env + 1] = p_high; }
   const bool ok = p_high > p_low;
   const double span = p_high - p_low;

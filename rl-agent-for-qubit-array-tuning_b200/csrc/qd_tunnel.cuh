@@ -1143,7 +1143,7 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
       }
       while (true) {
         int mb;
-        if (have_prev) {
+        if (have_prev && tau < INF && (a.topt & 2)) {
           // Warm-started list: tau is (nearly) final from the start, so the ORDER of the visits hardly matters -- take any
           // block whose bound is not above tau (one ballot instead of a 5-step (bound, index) reduction).  The set of
           // candidates that end up in the list does not depend on the order; the walk ends when no such block is left.
@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
 #pragma unroll 1
         for (int ii = 0; ii < LO_IT; ++ii) {
           const int i = (LO_IT >= 4) ? ((ii + LO_IT / 4) & (LO_IT - 1)) : ii;
-          if constexpr (NLO == 4) {
+          if (NLO == 4 && (a.topt & 1)) {
             // every candidate of this iteration has the leading low digit i >> 1: skip it when even the continuous minimum
             // over the other three low digits lies above the current 32nd-best energy
             const double y0 = (double)((i >> 1) - 1);
@@ -1481,7 +1481,7 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
       // Rayleigh quotients of the unit vectors, on the sector's own tridiagonal); a sector whose lower end exceeds the
       // smallest diagonal entry U of the whole matrix is out.  The multisection then runs over the lane range that covers
       // the candidate sectors only (the others inside that range have every eigenvalue above U: their minors stay positive).
-      double lo, hi;
+      double lo, hi, wfull;
       int c_lo, c_hi;
       {
         const double rad = ((lane > 0) ? fabs(ee[lane - 1]) : 0.0) + ((lane < 31) ? fabs(ee[lane]) : 0.0);
@@ -1495,13 +1495,13 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
           if (lane - d >= s0) ls = fmin(ls, t);
         }
         ls = shfl_f64(ls, s1);
-        const bool cand = ls <= U;
+        const bool cand = ls <= U || !(a.topt & 4);
         const unsigned cm = __ballot_sync(0xffffffffu, cand);          // never empty: the sector that owns U is in
         c_lo = __ffs(cm) - 1;
         c_hi = 31 - __clz(cm);
         lo = warp_min(cand ? lower : U);
         hi = U;
-        const double wfull = warp_max(dd[lane] + rad) - warp_min(lower);
+        wfull = warp_max(dd[lane] + rad) - warp_min(lower);
         // bracket width for the scaling below: not narrower than 1e-3 of the full Gershgorin width, so that the scaled
         // entries stay <= 1e3 in magnitude and the minors cannot overflow within a sector
         hi = fmax(hi, lo + 1e-3 * wfull);
@@ -1541,22 +1541,27 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
         if (j > 0) lo = xl;
         if (j < 32) hi = xh;
       }
-      lo = fma(lo, wid, lo0);
+      // The shift: the lower end of the final bracket, pushed down by 2e-12 of the Gershgorin width.  That is nothing for the
+      // convergence of the inverse iteration ((lambda_0 - mu) / (lambda_1 - mu) per step) but keeps T - mu I positive
+      // definite IN FLOATING POINT, four orders of magnitude above the rounding noise of the factorisation below: with the
+      // narrow bracket a shift within rounding of lambda_0 could otherwise meet a zero pivot.
+      lo = fma(lo, wid, lo0) - 2e-12 * wfull;
       __syncwarp();
       const double mu = lo;
+      const double qmin = fmax(1e-15 * wfull, 1e-300);       // pivot floor (never reached unless the matrix is degenerate)
       // LDL^T of T - mu I and the inverse-iteration solves, every sector by its own leader lane (the sectors are
       // decoupled: ee[s1] = 0), so the serial chains are one sector long instead of 32.
       if (lane == s0) {
         double q = dd[s0] - mu;
         for (int i = s0; i < s1; ++i) {
-          if (!(q > 0.0)) q = 1e-300;
+          if (!(q > qmin)) q = qmin;
           const double iq = 1.0 / q;
           qi[i] = iq;
           const double l = ee[i] * iq;
           ll[i] = l;
           q = (dd[i + 1] - mu) - l * ee[i];
         }
-        if (!(q > 0.0)) q = 1e-300;
+        if (!(q > qmin)) q = qmin;
         qi[s1] = 1.0 / q;
       }
       yy[lane] = 1.0 + (double)lane * (1.0 / 64.0);

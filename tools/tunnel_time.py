@@ -49,7 +49,9 @@ def main():
         ms = e0.elapsed_time(e1) / a.steps
         print(json.dumps({"tag": a.tag, "mono": os.environ.get("QDSIM_TUNNEL_MONO", "0"), "lib": os.environ.get("QDSIM_LIB", ""),
                           "n_dot": n_dot, "n_env": n_env, "pixels": pixels, "ms": ms, "Mpix_s": pixels / ms / 1e3,
-                          "env_steps_s": n_env / ms * 1e3, "nsum": float(n.double().sum().item())}), flush=True)
+                          "env_steps_s": n_env / ms * 1e3, "nsum": float(n.double().sum().item()),
+                          "nan_pixels": int(torch.isnan(n).any(dim=1).sum().item()), "opt": os.environ.get("QDSIM_TUNNEL_OPT", ""),
+                          "first_nan": (torch.isnan(n).any(dim=1).nonzero()[:4, 0].tolist())}), flush=True)
 
 
 if __name__ == "__main__":
