@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 #include "qd_kernels.cuh"
@@ -66,6 +67,9 @@ struct qd_ctx {
   long long up_pixels = 0;        // extent of the output buffers they address
   long long up_max_pix = 0;       // largest scan, in pixels
   int64_t launches = 0;
+  // QDSIM_TRACE=1: accumulated host-side phases of the small-call path (setup+launch, sync, copy-out), printed at destroy
+  double tr_launch = 0, tr_sync = 0, tr_copy = 0;
+  long tr_calls = 0;
 };
 
 namespace {
@@ -621,6 +625,9 @@ int qd_create(int device, qd_ctx** out) {
 
 void qd_destroy(qd_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->tr_calls > 0 && getenv("QDSIM_TRACE"))
+    fprintf(stderr, "[qdsim] small-call path: %ld calls, per call launch %.2f us, sync %.2f us, copy-out %.2f us\n", ctx->tr_calls,
+            ctx->tr_launch / ctx->tr_calls, ctx->tr_sync / ctx->tr_calls, ctx->tr_copy / ctx->tr_calls);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   if (ctx->d_records) cudaFree(ctx->d_records);
@@ -825,13 +832,22 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
     long long sum = 0;
     for (int i = 0; i < n_scan; ++i) sum += (long long)scans[i].nx * scans[i].ny;
     if (sum != pixels) memset(ctx->h_small, 0, need);          // gaps between scans read as zeros
+    using clk = std::chrono::steady_clock;
+    const auto t0 = clk::now();
     rc = launch(ctx, n_scan, ctx->d_scans, max_ny, nullptr, z_out_host ? (float*)ctx->d_small : nullptr,
                 ctx->d_small + zoff, n_type, flags, ctx->s_compute, 0, one ? scans : nullptr);
     if (rc) return rc;
+    const auto t1 = clk::now();
     QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    const auto t2 = clk::now();
     ctx->staged_pending = false;
     if (z_out_host) memcpy(z_out_host, ctx->h_small, zbytes);
     if (nbytes) memcpy(n_out_host, ctx->h_small + zoff, nbytes);
+    const auto t3 = clk::now();
+    ctx->tr_launch += std::chrono::duration<double, std::micro>(t1 - t0).count();
+    ctx->tr_sync += std::chrono::duration<double, std::micro>(t2 - t1).count();
+    ctx->tr_copy += std::chrono::duration<double, std::micro>(t3 - t2).count();
+    ctx->tr_calls += 1;
     return check_status(ctx);
   }
 

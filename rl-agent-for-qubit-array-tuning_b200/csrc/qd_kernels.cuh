@@ -550,14 +550,19 @@ struct BruteLevel {
                                              double emin, double inv_kT, double& Z, double (&acc)[N]) {
     const double dl = ud[LVL];
     const double ctr = g[LVL] - s[LVL];                     // continuous minimiser of this level's term
+    // children in order of increasing distance from the centre (Schnorr-Euchner zig-zag): the first leaf reached is the
+    // sequentially rounded point -- a strong incumbent -- and a level is left at its FIRST child that fails the bound,
+    // since every later child is farther from the centre
+    int up = (int)fmin(fmax(ceil(ctr), 0.0), (double)(maxc + 1));
+    int dn = up - 1;
 #pragma unroll 1
-    for (int v = 0; v <= maxc; ++v) {
+    while (dn >= 0 || up <= maxc) {
+      const bool take_up = dn < 0 || (up <= maxc && ((double)up - ctr) < (ctr - (double)dn));
+      const int v = take_up ? up : dn;
+      if (take_up) ++up; else --dn;
       const double y = (double)v - ctr;
       const double p = fma(dl * y, y, p_prev);
-      if (!(p < best)) {                                    // best: running minimum (PASS 0) / the 40 kT cut (PASS 1)
-        if ((double)v > ctr) break;                         // past the vertex: the term only grows from here
-        continue;
-      }
+      if (!(p < best)) break;                               // best: running minimum (PASS 0) / the 40 kT cut (PASS 1)
       const unsigned c2 = code * 16u + (unsigned)v;
       if constexpr (LVL == N - 1) {
         if constexpr (PASS == 0) {

@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_THERMAL, N_F64, maxwell
+from qdsim import FLAG_LATCH, FLAG_NOISE, FLAG_THERMAL, N_F64, N_U8, maxwell
 from qdsim.composer import GateVoltageComposer
 from qdsim.engine import ModelBatch, new_scans
 from qdsim.runtime import engine_for, fresh_seed
@@ -141,8 +141,11 @@ class ChargeSensedDotArray:
         s["nx"], s["ny"] = x_points, y_points
         if flags:                                   # the seed only feeds latching / noise draws
             s["seed"] = fresh_seed()
-        z, n = engine_for(self, self.device).scan_one_host(s, N_F64, flags)
-        return (z.astype(np.float64).reshape(y_points, x_points, 1), n.reshape(y_points, x_points, self.n_dot))
+        # hard argmin (T = 0): the occupations are small integers -- fetch them as one byte per dot (an eighth of the bytes
+        # the kernel has to push over PCIe) and widen here; thermal averages come back as float64
+        z, n = engine_for(self, self.device).scan_one_host(s, N_F64 if flags & FLAG_THERMAL else N_U8, flags)
+        return (z.astype(np.float64).reshape(y_points, x_points, 1),
+                n.astype(np.float64).reshape(y_points, x_points, self.n_dot))
 
     def do1d_open(self, gate, min, max, points):  # noqa: A002
         """1-d sweep, open array.  Returns ``(z (points, n_sensor), n (points, n_dot))``."""
