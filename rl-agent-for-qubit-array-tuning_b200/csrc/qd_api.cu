@@ -390,6 +390,17 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
   if (flags & QD_FLAG_CARRY_ROWS) rows = max_ny;
   a.rows_per_item = (int)rows;
   a.items_per_scan = (max_ny + a.rows_per_item - 1) / a.rows_per_item;
+  // A launch too small to give every SM a warp (a single do2d_open) is also split ALONG the rows when no state is carried
+  // from pixel to pixel (no latching, telegraph or 1/f chain): each item is then one 32-pixel chunk.
+  a.col_parts = 1;
+  if (!(flags & (QD_FLAG_LATCH | QD_FLAG_NOISE | QD_FLAG_PINK | QD_FLAG_CARRY_ROWS)) && rows == 1 &&
+      (long long)n_scan * a.items_per_scan < (long long)ctx->sm_count) {
+    const long long chunks_x = (ctx->up_max_pix / std::max(1, max_ny) + 31) / 32;      // 32-pixel chunks per row of the largest scan
+    long long cp = (long long)ctx->sm_count * 2 / std::max<long long>(1, (long long)n_scan * a.items_per_scan);
+    cp = std::min<long long>(std::max<long long>(cp, 1), std::max<long long>(chunks_x, 1));
+    a.col_parts = (int)cp;
+    a.items_per_scan *= a.col_parts;
+  }
   const long long total_items = (long long)n_scan * a.items_per_scan;
   // warps per CTA: the warps of a CTA are independent, but a CTA's slot (registers, shared memory) is only released when
   // its SLOWEST warp is done; scans differ in work (Gray-walk widths, latching events), so the restructured kernel runs

@@ -52,6 +52,8 @@ struct KArgs {
   int rows_per_item;
   int items_per_scan;
   int slot_bytes;
+  int col_parts;                       // items per row block along x (> 1 only when nothing is carried along a row: no
+                                       // latching, telegraph or 1/f chain) -- small launches spread over more SMs
 };
 
 constexpr int QD_DER_DOUBLES = 48;  // derived per-item block: g0[8] gx[8] gy[8] us0 usx usy pad[5] carry[8] + spare
@@ -753,9 +755,14 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
     }
 
     const int nx = sc->nx, ny = sc->ny;
-    const int row0 = part * a.rows_per_item;
+    const int cparts = a.col_parts > 1 ? a.col_parts : 1;
+    const int rpart = part / cparts, cpart = part - rpart * cparts;
+    const int row0 = rpart * a.rows_per_item;
     const int row1 = min(ny, row0 + a.rows_per_item);
-    if (row0 >= ny) { __syncwarp(); continue; }
+    // column range of this item: whole 32-pixel chunks, split evenly over the column parts
+    const int n_chunk_x = (nx + 31) >> 5;
+    const int cx0 = ((n_chunk_x * cpart) / cparts) << 5, cx1 = min(nx, ((n_chunk_x * (cpart + 1)) / cparts) << 5);
+    if (row0 >= ny || cx0 >= cx1) { __syncwarp(); continue; }
 
     // ---- affine coefficients of the dot potentials and of the sensor potential ----
     if constexpr (!POINTS) {
@@ -837,7 +844,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
 
     for (int iy = row0; iy < row1; ++iy) {
       if (!f_carry) { have_held = false; tele_init = false; pink_init = false; }
-      for (int c0 = 0; c0 < nx; c0 += 32) {
+      for (int c0 = cx0; c0 < cx1; c0 += 32) {
         const int ix = c0 + lane;
         const bool valid = ix < nx;
         const int ixc = valid ? ix : nx - 1;
@@ -1240,9 +1247,14 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_FAST_MIN_BLOCKS) qd_scan
     if (lane == 0) { pc.meta[0] = 0u; pc.meta[1] = 0u; }      // the projection cache belongs to one (env, window)
 
     const int nx = sc->nx, ny = sc->ny;
-    const int row0 = part * a.rows_per_item;
+    const int cparts = a.col_parts > 1 ? a.col_parts : 1;
+    const int rpart = part / cparts, cpart = part - rpart * cparts;
+    const int row0 = rpart * a.rows_per_item;
     const int row1 = min(ny, row0 + a.rows_per_item);
-    if (row0 >= ny) { __syncwarp(); continue; }
+    // column range of this item: whole 32-pixel chunks, split evenly over the column parts
+    const int n_chunk_x = (nx + 31) >> 5;
+    const int cx0 = ((n_chunk_x * cpart) / cparts) << 5, cx1 = min(nx, ((n_chunk_x * (cpart + 1)) / cparts) << 5);
+    if (row0 >= ny || cx0 >= cx1) { __syncwarp(); continue; }
 
     // ---- per-item affine forms: dot potentials, sensor potential, sum_j w_j g_j; the two nibble tables of w ----
     if (lane <= N) {
@@ -1297,7 +1309,7 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_FAST_MIN_BLOCKS) qd_scan
 
     for (int iy = row0; iy < row1; ++iy) {
       if (!f_carry) { have_held = false; tele_init = false; }
-      for (int c0 = 0; c0 < nx; c0 += 32) {
+      for (int c0 = cx0; c0 < cx1; c0 += 32) {
         const int ix = c0 + lane;
         const bool valid = ix < nx;
         const int ixc = valid ? ix : nx - 1;

@@ -136,9 +136,16 @@ class ChargeSensedDotArray:
         ng = self.n_gate
         v0v, dxv, dyv = d["_scan1_views"]
         v0v[:ng], dxv[:ng], dyv[:ng] = aff
-        flags = self._flags(True)
-        s["peak_width"] = float(self.coulomb_peak_width)
-        s["nx"], s["ny"] = x_points, y_points
+        fl = d.get("_flags_cache")
+        if fl is None or fl[0] != self._version:
+            fl = d["_flags_cache"] = (self._version, self._flags(True))
+        flags = fl[1]
+        pw = float(self.coulomb_peak_width)
+        last = d.get("_scan1_last")
+        if last != (pw, x_points, y_points):
+            s["peak_width"] = pw
+            s["nx"], s["ny"] = x_points, y_points
+            d["_scan1_last"] = (pw, x_points, y_points)
         if flags:                                   # the seed only feeds latching / noise draws
             s["seed"] = fresh_seed()
         # hard argmin (T = 0): the occupations are small integers -- fetch them as one byte per dot (an eighth of the bytes
