@@ -324,7 +324,27 @@ def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_e
     return blk
 
 
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything any library prints to fd 1 during the run (NCCL prints its version line there) goes to stderr; the ONE
+    JSON line is written to the real stdout by ``_emit``."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(obj):
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -383,7 +403,7 @@ def main():
         dt = sum(t for _, t in timed)
         value = pixels / dt
         sample = f"{n_scans} scans ({timed[0][0]} pixels) of the workload per step"
-        print(json.dumps({
+        _emit(({
             "impl": "reference", "metric": "ground_state_pixels_per_s", "value": value, "unit": "pixels/s",
             "env_steps_per_s": value / pix_per_env, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / max(1, len(timed)), "higher_is_better": True, "scaling": "weak",
@@ -508,6 +528,18 @@ def main():
         return max(per_rank), per_rank
 
     e2e_ms, e2e_ranks = time_e2e(e2e_step)
+    # the measured host ceiling of this copy (profiles/r02_d2h_ceiling.json: every rank of one box copying at once)
+    ceiling = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_d2h_ceiling.json")) as f:
+            c = json.load(f)["by_ranks"].get(str(world))
+        if c:
+            ms_c = pixels * 4 / (min(c["d2h_per_rank_gbs"]) * 1e9) * 1e3
+            ceiling = {"d2h_gbs_slowest_rank": min(c["d2h_per_rank_gbs"]), "ms_per_step_copy_only": ms_c,
+                       "frac_of_ceiling": ms_c / e2e_ms,
+                       "source": "profiles/r02_d2h_ceiling.json (tools/pcie_bw.py, all ranks copying concurrently)"}
+    except (OSError, ValueError, KeyError):
+        pass
     clocks = sampler.stop() if rank == 0 else None          # sampled across the device-resident and the fp32 e2e regions
     e2e_value = world * pixels / (e2e_ms * 1e-3)
     compact = {}
@@ -596,7 +628,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "pixels/s", "env_steps_per_s": e2e_value / pix_per_env,
                     "ms_per_step": e2e_ms, "per_rank_ms": e2e_ranks, "format": "fp32 sensor images (the parity format)",
                     "h2d_bytes_per_step": int(sets[0].nbytes), "d2h_bytes_per_step": int(pixels * 4),
-                    "matches_device_resident_launch": e2e_same},
+                    "matches_device_resident_launch": e2e_same, "host_d2h_ceiling": ceiling},
             "e2e_compact": compact or None,
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity,
             "parity_note": "latching / noise semantics are the restatement's (qarray wheel absent: parity unpinned there, "
@@ -621,7 +653,7 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out))
+        _emit(out)
 
 
 if __name__ == "__main__":
