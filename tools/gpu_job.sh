@@ -12,6 +12,10 @@ $T > $o/${tag}_plainB.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-c
 ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_select -s 2 -c 1 -o $o/prof_${tag}_select8 $T > $o/${tag}_ncuS.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_eigen -s 2 -c 1 -o $o/prof_${tag}_eigen8 $T > $o/${tag}_ncuE.log 2>&1
 tools/ncu_export.sh $o/prof_${tag}_fast8 $o/prof_${tag}_select8 $o/prof_${tag}_eigen8
-python tools/sweep.py --quick > $o/${tag}_sweep_quick.json 2> $o/${tag}_sweep.err
+python tools/sweep.py > $o/${tag}_sweep.json 2> $o/${tag}_sweep.err
+QDSIM_TRACE=1 python tools/latency.py > $o/${tag}_latency.json 2> $o/${tag}_latency.err
+python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference.json 2>/dev/null
+python bench.py --path B --n-dot 4 --n-env 1024 --no-compact --parity-scans 0 > $o/${tag}_bench_pathB_4dot.json 2> $o/${tag}_bench_pathB.err
+nvidia-smi --query-gpu=name,driver_version,clocks.max.sm,clocks.max.mem,memory.total,power.limit --format=csv > $o/${tag}_gpu_info.csv
 python tools/shell_breakdown.py > $o/${tag}_shell_breakdown.txt 2>&1
 du -sh $o
