@@ -255,20 +255,34 @@ def tunnel_cpu_baseline(mb, scans, budget_s: float = 8.0):
                     "OpenMP over pixels"}
 
 
-def issue_roofline(kernel: str, pixels_per_s: float, sm_count: int, sm_mhz: float):
-    """Issue-slot roofline of a kernel with data-dependent control flow (no flop model): warp instructions per pixel from
-    the committed ncu capture of THIS source (profiles/ncu_figures.json, keyed by source hash) against 4 issue slots per SM
-    per clock at the measured SM clock."""
-    fig = ncu_figure(kernel)
-    if not fig or not fig.get("warp_instr_per_pixel"):
-        return {"kernel": kernel, "bound": "issue", "achieved": None, "peak": None, "frac": None,
-                "note": "no ncu figure committed for this kernel (profiles/ncu_figures.json)"}
+def issue_roofline(kernels, pixels_per_s: float, sm_count: int, sm_mhz: float):
+    """Issue-slot roofline of kernels with data-dependent control flow (no flop model): warp instructions per pixel from
+    the committed ncu captures of THIS source (profiles/ncu_figures.json, keyed by source hash), summed over the kernels of
+    the pipeline, against 4 issue slots per SM per clock at the measured SM clock."""
+    if isinstance(kernels, str):
+        kernels = [kernels]
+    figs = {k: ncu_figure(k) for k in kernels}
+    missing = [k for k, f in figs.items() if not f or not f.get("warp_instr_per_pixel")]
+    name = " + ".join(kernels)
+    if missing:
+        return {"kernel": name, "bound": "issue", "achieved": None, "peak": None, "frac": None,
+                "note": f"no ncu figure committed for {missing} (profiles/ncu_figures.json)"}
+    instr = sum(f["warp_instr_per_pixel"] for f in figs.values())
+    traffic = sum((f.get("dram_bytes_per_pixel") or 0.0) for f in figs.values())
     peak = sm_count * 4 * sm_mhz * 1e6
-    ach = pixels_per_s * fig["warp_instr_per_pixel"]
-    return {"kernel": kernel, "bound": "issue", "achieved": ach, "peak": peak, "unit": "warp-instr/s", "frac": ach / peak,
-            "warp_instr_per_pixel": fig["warp_instr_per_pixel"], "source": fig.get("source"),
-            "figure_source_sha": fig.get("source_sha"), "stale": fig["stale"], "traffic": fig.get("dram_bytes_per_pixel"),
-            "ncu_issue_active_pct": fig.get("issue_active_pct")}
+    ach = pixels_per_s * instr
+    return {"kernel": name, "bound": "issue", "achieved": ach, "peak": peak, "unit": "warp-instr/s", "frac": ach / peak,
+            "warp_instr_per_pixel": instr, "per_kernel": {k: {"warp_instr_per_pixel": f["warp_instr_per_pixel"],
+                                                               "ncu_issue_active_pct": f.get("issue_active_pct"),
+                                                               "registers": f.get("registers")} for k, f in figs.items()},
+            "source": "ncu --set full captures listed in profiles/ncu_figures.json",
+            "figure_source_sha": sorted({f.get("source_sha") for f in figs.values()}),
+            "stale": any(f["stale"] for f in figs.values()), "traffic": traffic,
+            "traffic_note": "DRAM bytes per pixel of the listed kernels (dram__bytes_read.sum + dram__bytes_write.sum)"}
+
+
+def tunnel_kernels(n_dot: int):
+    return [f"qd_tunnel_select_kernel<{n_dot}>", f"qd_tunnel_eigen_kernel<{n_dot}>"]
 
 
 def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_env: int = 512, steps: int = 5,
@@ -311,13 +325,13 @@ def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_e
     props = torch.cuda.get_device_properties(0)
     blk = {"workload": f"{n_dot}-dot tunnel-coupled array (TunnelCoupledChargeSensed, 32-state basis, barrier voltages), "
                        f"{n_env} envs, {n_dot - 1} scans/env of {res}x{res}, latching + noise",
-           "kernels": f"qd_tunnel_gs_kernel<{n_dot}> + qd_scan_kernel<{n_dot},tunnel>",
+           "kernels": f"qd_tunnel_relax_kernel<{n_dot}> + qd_tunnel_select_kernel<{n_dot}> + qd_tunnel_eigen_kernel<{n_dot}> "
+                      f"+ qd_scan_kernel<{n_dot},tunnel>",
            "value": pixels / (ms * 1e-3), "unit": "pixels/s", "env_steps_per_s": n_env / (ms * 1e-3),
            "ms_per_step": ms, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),
            "e2e": {"value": pixels / (e2e_ms * 1e-3), "unit": "pixels/s", "env_steps_per_s": n_env / (e2e_ms * 1e-3),
                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(scans.nbytes), "d2h_bytes_per_step": int(pixels * 4)},
-           "roofline": issue_roofline(f"qd_tunnel_gs_kernel<{n_dot}>", pixels / (ms * 1e-3), props.multi_processor_count,
-                                      sm_mhz),
+           "roofline": issue_roofline(tunnel_kernels(n_dot), pixels / (ms * 1e-3), props.multi_processor_count, sm_mhz),
            "cpu_baseline": None}
     if with_cpu:
         blk["cpu_baseline"] = tunnel_cpu_baseline(mb, scans)
@@ -597,7 +611,7 @@ def main():
         }
         cpu = None
         if args.path == "B":
-            roofline = issue_roofline(f"qd_tunnel_gs_kernel<{N}>", pix_s_kernel, sm_count, sm_mhz)
+            roofline = issue_roofline(tunnel_kernels(N), pix_s_kernel, sm_count, sm_mhz)
             roofline["kernel_ms"] = k_ms
             if world == 1 and not args.no_cpu_baseline:
                 cpu = tunnel_cpu_baseline(mb, sets[0])

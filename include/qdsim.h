@@ -77,14 +77,25 @@ typedef struct qd_env_params {
   double p_inter[QD_MAX_DOTS * QD_MAX_DOTS]; /* LatchingModel.p_inter, row-major, stride QD_MAX_DOTS        */
   double tc_base;                          /* BarrierVoltageModel.tc_base            (QD_ALG_TUNNEL)        */
   double alpha[QD_MAX_DOTS];               /* BarrierVoltageModel.alpha[n_barrier]   (QD_ALG_TUNNEL)        */
-  double vc_alpha, vc_beta;                /* create_linear_capacitance_model(alpha, beta) (QD_ALG_TUNNEL):  */
-                                           /* cdd *= 1 + vc_alpha mean|v|, cgd *= 1 + vc_beta mean|v| per    */
-                                           /* pixel in the ground state (voltage_dependent_capacitance.py:   */
-                                           /* 78-91, 128-141); 0, 0 = constant capacitances                  */
+  double vc_alpha, vc_beta;                /* voltage-dependent capacitances (QD_ALG_TUNNEL), per pixel in   */
+                                           /* the ground state: cdd *= s_c(v; vc_kind, vc_alpha [, vc_vchar]), */
+                                           /* cgd *= 1 + vc_beta mean|v| (voltage_dependent_capacitance.py:   */
+                                           /* 78-167); 0, 0 = constant capacitances                          */
   int32_t max_charge_carriers;             /* brute_force                                                   */
   int32_t latching;                        /* 0: env has no LatchingModel                                   */
   double pink_amp;                         /* QD_FLAG_PINK: standard deviation of the 1/f input-noise term   */
+  double vc_vchar;                         /* vc_kind = sigmoid: characteristic voltage v_char                */
+  int32_t vc_kind;                         /* enum qd_vc_kind: how vc_alpha scales cdd (see below)            */
+  int32_t reserved0;
 } qd_env_params;
+
+/* Voltage-dependent capacitance models of the tunnel path (voltage_dependent_capacitance.py:78-167).  In all of them
+ * cgd scales by 1 + vc_beta mean|v|; cdd scales by
+ *   QD_VC_LINEAR     1 + vc_alpha mean|v|                                   (create_linear_capacitance_model, :123-135)
+ *   QD_VC_QUADRATIC  1 + vc_alpha sum v^2           (vc_alpha = gamma)      (create_quadratic_capacitance_model, :138-151)
+ *   QD_VC_SIGMOID    1 + vc_alpha sigmoid(|v|_2 / vc_vchar - 1)  (vc_alpha = delta)   (create_sigmoid_..., :154-168)
+ * over ALL entries of the pixel's voltage vector (ground_state.py:53-58). */
+enum qd_vc_kind { QD_VC_LINEAR = 0, QD_VC_QUADRATIC = 1, QD_VC_SIGMOID = 2 };
 
 /* Shape and algorithm of a model set (all envs of one set share them). */
 typedef struct qd_model_desc {

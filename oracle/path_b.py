@@ -143,7 +143,13 @@ def ground_state_open(m, v_ext, return_gap: bool = False, chunk: int = 128):
         s_c = None
         if getattr(m, "vc_alpha", 0.0) or getattr(m, "vc_beta", 0.0):
             vmean = np.abs(v).mean(axis=1)
-            s_c = 1.0 + m.vc_alpha * vmean
+            kind = int(getattr(m, "vc_kind", 0))
+            if kind == 1:      # quadratic_voltage_dependent_cdd, voltage_dependent_capacitance.py:94-99
+                s_c = 1.0 + m.vc_alpha * (v ** 2).sum(axis=1)
+            elif kind == 2:    # sigmoid_voltage_dependent_cdd, :102-109 (jax.nn.sigmoid(x) = 1 / (1 + exp(-x)))
+                s_c = 1.0 + m.vc_alpha / (1.0 + np.exp(1.0 - np.linalg.norm(v, axis=1) / m.vc_vchar))
+            else:              # linear_voltage_dependent_cdd, :78-83
+                s_c = 1.0 + m.vc_alpha * vmean
             g = g * (1.0 + m.vc_beta * vmean)[:, None]
         n_c = continuous_ground_state(g, cinv, s_c)
         states = select_charge_states(g, n_c, cinv, m.num_charge_states, m.charge_state_batch_size)   # order is scale-free

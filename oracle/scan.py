@@ -43,6 +43,8 @@ class Model:
     charge_state_batch_size: int = 1000
     vc_alpha: float = 0.0          # create_linear_capacitance_model(alpha, beta); 0, 0 = constant capacitances
     vc_beta: float = 0.0
+    vc_kind: int = 0               # 0 linear, 1 quadratic (vc_alpha = gamma), 2 sigmoid (vc_alpha = delta, vc_vchar = v_char)
+    vc_vchar: float = 1.0
 
 
 @dataclass

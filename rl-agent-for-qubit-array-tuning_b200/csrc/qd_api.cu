@@ -710,6 +710,10 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
       return fail(ctx, QD_ERR_UNSUPPORTED, "env %d: voltage-dependent capacitances exist on the tunnel path only", e);
     if (!(p.vc_alpha >= 0.0) || !(p.vc_beta >= 0.0))
       return fail(ctx, QD_ERR_INVALID, "env %d: vc_alpha / vc_beta must be >= 0", e);
+    if (p.vc_kind < QD_VC_LINEAR || p.vc_kind > QD_VC_SIGMOID)
+      return fail(ctx, QD_ERR_INVALID, "env %d: vc_kind %d is not a qd_vc_kind", e, p.vc_kind);
+    if (p.vc_kind == QD_VC_SIGMOID && p.vc_alpha != 0.0 && !(p.vc_vchar > 0.0))
+      return fail(ctx, QD_ERR_INVALID, "env %d: the sigmoid capacitance model needs vc_vchar > 0", e);
     memcpy(r + L.o_cinv, cdd_inv_gs + (size_t)e * N * N, sizeof(double) * N * N);
     if (cdd_gs) memcpy(r + L.o_cdd, cdd_gs + (size_t)e * N * N, sizeof(double) * N * N);
     const double* cg = cgd_full + (size_t)e * D * NV;
@@ -733,6 +737,8 @@ int qd_set_models(qd_ctx* ctx, const qd_model_desc* desc, const double* cdd_inv_
     par[QD_PAR_VC_ALPHA] = p.vc_alpha;
     par[QD_PAR_VC_BETA] = p.vc_beta;
     par[QD_PAR_PINK] = p.pink_amp;
+    par[QD_PAR_VC_KIND] = (double)p.vc_kind;
+    par[QD_PAR_VC_VCHAR] = p.vc_vchar;
     for (int j = 0; j < 8; ++j) r[L.o_alpha + j] = p.alpha[j];
     for (int j = 0; j < 8; ++j) r[L.o_pleads + j] = p.p_leads[j];
     for (int j = 0; j < 64; ++j) r[L.o_pinter + j] = p.p_inter[j];

@@ -596,7 +596,8 @@ struct BruteLevel<N, N> {
 // `ud`: d[8] | U[64] of cdd_inv with rows / columns permuted by `pm` (pm[l] = dot at tree level l, pm[8 + j] = level of dot
 // j); `gp`: the potentials in that order.  The order is chosen per work item (most negative potential first): a dot far below
 // its first transition is pinned to 0 carriers, and with it at the TOP of the tree its unavoidable cost sits in every
-// partial sum and conditions the centres of the levels below -- the bound bites.  (With such dots at the bottom the
+// partial sum and conditions the centres of the levels below -- the bound bites (likewise a dot far above max_charge_carriers,
+// pinned to the upper face).  (With such dots at the bottom the
 // unconstrained completion the bound assumes is far below anything the box allows, and the walk degenerates.)
 // Exact energy ties (measure zero; the parity tests skip margins <= 1e-9) resolve in tree order.
 template <int N, bool THERMAL>
@@ -794,9 +795,13 @@ __global__ void __launch_bounds__(QD_CTA_WARPS * 32, QD_MIN_BLOCKS) qd_scan_kern
       if (lane == 0) {
         int ord[N];
         double gc[N];
+        const double maxc_d = rec[L.o_par + QD_PAR_MAXC];
         for (int j = 0; j < N; ++j) {
           ord[j] = j;
-          gc[j] = POINTS ? 0.0 : fma(0.5 * (double)(row0 + row1 - 1), d_gy[j], fma(0.5 * (double)(nx - 1), d_gx[j], d_g0[j]));
+          // sort key: how far INSIDE the box [0, maxc] the potential at the item's centre lies (negative: outside, pinned to
+          // a face -- those dots go to the top of the tree, the most firmly pinned first)
+          const double gcj = POINTS ? 0.0 : fma(0.5 * (double)(row0 + row1 - 1), d_gy[j], fma(0.5 * (double)(nx - 1), d_gx[j], d_g0[j]));
+          gc[j] = fmin(gcj, maxc_d - gcj);
         }
         if (!POINTS) {
           for (int i = 1; i < N; ++i) {                    // insertion sort by potential, ascending

@@ -20,7 +20,9 @@ enum {
   QD_PAR_VC_ALPHA = 10,   // linear voltage-dependent capacitance model (tunnel path), 0 = off
   QD_PAR_VC_BETA = 11,
   QD_PAR_PINK = 12,       // amplitude of the 1/f input-noise term (QD_FLAG_PINK)
-  QD_PAR_COUNT = 14       // (even: the blocks after `par` stay 16-byte aligned)
+  QD_PAR_VC_KIND = 13,    // enum qd_vc_kind
+  QD_PAR_VC_VCHAR = 14,   // sigmoid model: characteristic voltage
+  QD_PAR_COUNT = 16       // (even: the blocks after `par` stay 16-byte aligned)
 };
 
 struct qd_layout {

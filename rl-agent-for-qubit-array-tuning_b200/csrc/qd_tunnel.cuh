@@ -36,6 +36,17 @@ __host__ __device__ inline int qd_tunnel_slot_bytes(const qd_layout& L) {
   return (b + 127) & ~127;
 }
 
+// Scales of the voltage-dependent capacitance models (voltage_dependent_capacitance.py:78-125; include/qdsim.h enum
+// qd_vc_kind): cdd -> s_c cdd, cgd -> s_g cgd, from sum|v_k| and sum v_k^2 over ALL voltages of the pixel.
+__device__ __forceinline__ void vc_scales(const double* __restrict__ par, double vabs, double v2, int NV, double& s_c, double& s_g) {
+  const double vmean = vabs / (double)NV;
+  s_g = fma(par[QD_PAR_VC_BETA], vmean, 1.0);
+  const int kind = (int)par[QD_PAR_VC_KIND];
+  if (kind == QD_VC_QUADRATIC) s_c = fma(par[QD_PAR_VC_ALPHA], v2, 1.0);
+  else if (kind == QD_VC_SIGMOID) s_c = 1.0 + par[QD_PAR_VC_ALPHA] / (1.0 + exp(1.0 - sqrt(v2) / par[QD_PAR_VC_VCHAR]));
+  else s_c = fma(par[QD_PAR_VC_ALPHA], vmean, 1.0);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -303,11 +314,11 @@ __global__ void __launch_bounds__(128, 3) qd_tunnel_gs_kernel(const KArgs a) {
               if (vc_on) {
                 // linear voltage-dependent capacitances (voltage_dependent_capacitance.py:78-91): cgd scales by
                 // 1 + beta mean|v|, cdd by 1 + alpha mean|v| (so cdd^-1 by its inverse)
-                double vabs = 0.0;
-                for (int k = 0; k < NV; ++k) vabs += fabs(vv[k]);
-                const double vmean = vabs / (double)NV;
-                acc *= fma(par[QD_PAR_VC_BETA], vmean, 1.0);
-                if (lane == 0) ts[7] = fma(par[QD_PAR_VC_ALPHA], vmean, 1.0);
+                double vabs = 0.0, v2 = 0.0, s_c, s_g;
+                for (int k = 0; k < NV; ++k) { vabs += fabs(vv[k]); v2 = fma(vv[k], vv[k], v2); }
+                vc_scales(par, vabs, v2, NV, s_c, s_g);
+                acc *= s_g;
+                if (lane == 0) ts[7] = s_c;
               }
               gs[lane] = acc;
             }
@@ -818,21 +829,22 @@ __global__ void __launch_bounds__(128) qd_tunnel_relax_kernel(const KArgs a) {
       double g[N];
 #pragma unroll
       for (int j = 0; j < N; ++j) g[j] = 0.0;
-      double vabs = 0.0;
+      double vabs = 0.0, v2 = 0.0;
       for (int k = 0; k < NV; ++k) {
         const double vk = (a.points == nullptr) ? fma((double)iy, sc->dy[k], fma((double)ix, sc->dx[k], sc->v0[k]))
                                                 : a.points[(size_t)pix * NV + k];
         vabs += fabs(vk);
+        v2 = fma(vk, vk, v2);
 #pragma unroll
         for (int j = 0; j < N; ++j) g[j] = fma(rec[L.o_a + j * NV + k], vk, g[j]);
       }
       double lr = 0.1;
       if (vc_on) {
-        const double vmean = vabs / (double)NV;
-        const double sb = fma(par[QD_PAR_VC_BETA], vmean, 1.0);
+        double s_c, sb;
+        vc_scales(par, vabs, v2, NV, s_c, sb);
 #pragma unroll
         for (int j = 0; j < N; ++j) g[j] *= sb;
-        lr = 0.1 / fma(par[QD_PAR_VC_ALPHA], vmean, 1.0);
+        lr = 0.1 / s_c;
       }
       bool neg = false;
       double n[N];
@@ -1044,7 +1056,7 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
         if (vc_on) {
           double vabs = 0.0;
           for (int k = 0; k < NV; ++k) vabs += fabs(vv[k]);
-          acc *= fma(par[QD_PAR_VC_BETA], vabs / (double)NV, 1.0);
+          acc *= fma(par[QD_PAR_VC_BETA], vabs / (double)NV, 1.0);          // (s_g is the same in every model)
         }
         gs[lane] = acc;
         const double fj = (double)(unsigned)((fk >> (8 * lane)) & 0xffu);
@@ -1324,11 +1336,11 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
           const double* arow = rec + L.o_a + lane * NV;
           for (int k = 0; k < NV; ++k) acc = fma(arow[k], vv[k], acc);
           if (vc_on) {
-            double vabs = 0.0;
-            for (int k = 0; k < NV; ++k) vabs += fabs(vv[k]);
-            const double vmean = vabs / (double)NV;
-            acc *= fma(par[QD_PAR_VC_BETA], vmean, 1.0);
-            if (lane == 0) ts[7] = fma(par[QD_PAR_VC_ALPHA], vmean, 1.0);
+            double vabs = 0.0, v2 = 0.0, s_c, s_g;
+            for (int k = 0; k < NV; ++k) { vabs += fabs(vv[k]); v2 = fma(vv[k], vv[k], v2); }
+            vc_scales(par, vabs, v2, NV, s_c, s_g);
+            acc *= s_g;
+            if (lane == 0) ts[7] = s_c;
           }
           gs[lane] = acc;
         }

@@ -104,11 +104,13 @@ class TunnelCoupledChargeSensed:
         if vcm is not None:
             # the linear model of create_linear_capacitance_model as the facade builds it (qarray_base_class.py:846-851:
             # cdd_0 = model.cdd_full, cgd_0 = model.cgd_full): two scalars per env, applied per pixel in the kernel
-            if getattr(vcm, "kind", None) != "linear":
-                raise NotImplementedError("only the linear voltage-dependent capacitance model is wired into the kernel")
+            if getattr(vcm, "kind", None) not in ("linear", "quadratic", "sigmoid"):
+                raise NotImplementedError("voltage-dependent capacitance models: linear, quadratic and sigmoid (the "
+                                          "reference's factories) are wired into the kernel; build one with "
+                                          "qarray_latched.DotArrays.voltage_dependent_capacitance.create_*_capacitance_model")
             if not (np.allclose(vcm.cdd_0, self.cdd_full, rtol=1e-12, atol=0) and
                     np.allclose(vcm.cgd_0, self.cgd_full, rtol=1e-12, atol=0)):
-                raise NotImplementedError("the linear capacitance model must be built on the model's own cdd_full / "
+                raise NotImplementedError("the capacitance model must be built on the model's own cdd_full / "
                                           "cgd_full (as qarray_base_class.py:846-851 does)")
         if not isinstance(self.num_charge_states, int):
             raise NotImplementedError("num_charge_states=None builds a dense 5^N x 5^N Hamiltonian per pixel in the "
@@ -135,6 +137,8 @@ class TunnelCoupledChargeSensed:
             params["tc_base"] = self.tc                   # constant nearest-neighbour coupling (ground_state.py:92-101)
         if vcm is not None:
             params["vc_alpha"], params["vc_beta"] = vcm.alpha, vcm.beta
+            params["vc_kind"] = {"linear": 0, "quadratic": 1, "sigmoid": 2}[vcm.kind]
+            params["vc_vchar"] = getattr(vcm, "v_char", 1.0)
         cbg = None
         if use_barriers:
             cbg = np.zeros((1, self.n_barrier, self.n_gate)) if self.Cbg is None else self.Cbg[None]

@@ -41,8 +41,10 @@ PARAMS_DTYPE = np.dtype([
     ("p_leads", "f8", (QD_MAX_DOTS,)), ("p_inter", "f8", (QD_MAX_DOTS * QD_MAX_DOTS,)),
     ("tc_base", "f8"), ("alpha", "f8", (QD_MAX_DOTS,)), ("vc_alpha", "f8"), ("vc_beta", "f8"),
     ("max_charge_carriers", "i4"), ("latching", "i4"), ("pink_amp", "f8"),
+    ("vc_vchar", "f8"), ("vc_kind", "i4"), ("reserved0", "i4"),
 ], align=True)
-assert PARAMS_DTYPE.itemsize == 728, PARAMS_DTYPE.itemsize
+assert PARAMS_DTYPE.itemsize == 744, PARAMS_DTYPE.itemsize
+VC_LINEAR, VC_QUADRATIC, VC_SIGMOID = 0, 1, 2
 
 
 class ModelDesc(C.Structure):

@@ -37,6 +37,11 @@ CASES = {
     # voltage_capacitance_model.type: linear (qarray_config.yaml:103-105, 132-134; qarray_base_class.py:842-852)
     "ref_4dot_tunnel_linear_capacitance": dict(n_dot=4, res=20, seed=17, pair=2, vgm="identity", cbb=False, vc=(0.08, 0.06)),
     "ref_6dot_tunnel_linear_capacitance": dict(n_dot=6, res=12, seed=18, pair=3, vgm="perfect", cbb=False, vc=(0.05, 0.10)),
+    # the reference's other factories (voltage_dependent_capacitance.py:138-168; unreachable from the shipped facade)
+    "ref_4dot_tunnel_quadratic_capacitance": dict(n_dot=4, res=16, seed=22, pair=2, vgm="identity", cbb=False, vc=(0.004, 0.05),
+                                                  vc_kind="quadratic"),
+    "ref_5dot_tunnel_sigmoid_capacitance": dict(n_dot=5, res=14, seed=23, pair=2, vgm="identity", cbb=False, vc=(0.4, 0.03),
+                                                vc_kind="sigmoid", vc_vchar=4.0),
     # the env's own regime (env.py:808-858): barriers up to +-15 V from their optimum, i.e. tunnel couplings from 1e-9 to 1e7,
     # and windows tens of volts from the ground truth (occupations of 10-40 carriers on some dots, none on others)
     "ref_4dot_tunnel_strong_coupling": dict(n_dot=4, res=16, seed=19, pair=2, vgm="identity", cbb=False, vb_shift=-8.0),
@@ -47,7 +52,8 @@ CASES = {
 }
 
 
-def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True, vc=None, vb_shift=0.0, spread=2.0):
+def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True, vc=None, vb_shift=0.0, spread=2.0,
+                vc_kind="linear", vc_vchar=1.0):
     """Raw inputs of one case, drawn with the reference's sampling ranges (qdsim.synth)."""
     from qdsim import synth
     dev = synth.sample_barrier_devices(1, n_dot, seed=seed)
@@ -63,7 +69,8 @@ def case_inputs(n_dot, res, seed, pair, vgm, cbb, offset=0.0, barriers=True, vc=
     raw["barrier_voltages"] = rng.uniform(-1.0, 3.0, size=B) + vb_shift
     raw["half"] = float(rng.uniform(1.5, 2.0))
     raw["centre_offset"] = rng.uniform(-spread, spread, size=n_dot) + offset
-    raw.update(res=res, pair=pair, vgm_kind=vgm, vc=np.array(vc if vc is not None else (0.0, 0.0)))
+    raw.update(res=res, pair=pair, vgm_kind=vgm, vc=np.array(vc if vc is not None else (0.0, 0.0)),
+               vc_kind=np.array({"linear": 0, "quadratic": 1, "sigmoid": 2}[vc_kind]), vc_vchar=np.array(float(vc_vchar)))
     return raw
 
 
@@ -85,9 +92,17 @@ def run_reference(raw):
         if raw["vc"].any():                              # qarray_base_class.py:846-852
             vdc = sys.modules["qarray_latched.DotArrays.voltage_dependent_capacitance"]
             import jax.numpy as jnp
-            model.voltage_capacitance_model = vdc.create_linear_capacitance_model(
-                cdd_0=jnp.array(model.cdd_full), cgd_0=jnp.array(model.cgd_full), alpha=float(raw["vc"][0]),
-                beta=float(raw["vc"][1]))
+            c0, g0 = jnp.array(model.cdd_full), jnp.array(model.cgd_full)
+            kind = int(raw.get("vc_kind", 0))
+            if kind == 1:
+                model.voltage_capacitance_model = vdc.create_quadratic_capacitance_model(
+                    cdd_0=c0, cgd_0=g0, gamma=float(raw["vc"][0]), beta=float(raw["vc"][1]))
+            elif kind == 2:
+                model.voltage_capacitance_model = vdc.create_sigmoid_capacitance_model(
+                    cdd_0=c0, cgd_0=g0, v_char=float(raw["vc_vchar"]), delta=float(raw["vc"][0]), beta=float(raw["vc"][1]))
+            else:
+                model.voltage_capacitance_model = vdc.create_linear_capacitance_model(
+                    cdd_0=c0, cgd_0=g0, alpha=float(raw["vc"][0]), beta=float(raw["vc"][1]))
         comp = model.gate_voltage_composer
         perfect_vgm = np.array(comp.virtual_gate_matrix)
         if raw["vgm_kind"] == "identity":                # qarray_base_class.py:868-877 (electrons: -I)

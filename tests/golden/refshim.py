@@ -160,6 +160,7 @@ def make_jax():
     sparse.BCOO = type("BCOO", (), {})                  # annotation target only (use_sparse is False)
     jax.jit, jax.vmap = _jit, _vmap
     jax.config = types.SimpleNamespace(update=lambda *a, **k: None)
+    jax.nn = types.SimpleNamespace(sigmoid=lambda x: 1.0 / (1.0 + np.exp(-np.asarray(x, dtype=np.float64))))   # definition
     jax.devices = lambda *a, **k: []
     return {"jax": jax, "jax.numpy": jnp, "jax.numpy.linalg": linalg, "jax.lax": lax, "jax.experimental": exp,
             "jax.experimental.sparse": sparse}

@@ -27,6 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_CASES = ["ref_4dot_tunnel_identity_vgm", "ref_4dot_tunnel_perfect_vgm_cbb", "ref_5dot_tunnel_low_occupancy",
              "ref_6dot_tunnel_identity_vgm", "ref_8dot_tunnel_identity_vgm", "ref_4dot_constant_tc_no_barriers",
              "ref_4dot_tunnel_linear_capacitance", "ref_6dot_tunnel_linear_capacitance",
+             "ref_4dot_tunnel_quadratic_capacitance", "ref_5dot_tunnel_sigmoid_capacitance",
              "ref_4dot_tunnel_strong_coupling", "ref_4dot_tunnel_closed_barriers", "ref_6dot_tunnel_far_window"]
 GAP_TOL = 1e-6            # spectral gap below which <n> is not unique
 N_ATOL_CPU = 1e-11        # LAPACK (reference run) vs LAPACK (oracle); measured 5e-14
@@ -52,6 +53,8 @@ def product_model(d):
                                 d["Cbg"][None], d["Cbs"][None], float(d["tc_base"]), d["alpha"][None])
         if "vc" in d:
             mb.params["vc_alpha"], mb.params["vc_beta"] = d["vc"]
+            mb.params["vc_kind"] = int(d["vc_kind"]) if "vc_kind" in d else 0
+            mb.params["vc_vchar"] = float(d["vc_vchar"]) if "vc_vchar" in d else 1.0
         return mb
     cdd_nm, cgd_nm = maxwell.embed_sensor(d["Cdd"][None], d["Cgd"][None], d["Cds"][None], d["Cgs"][None])
     _, cdd_inv_full, cgd_full = maxwell.maxwell(cdd_nm, cgd_nm)
@@ -152,9 +155,18 @@ def _drop_in(d, device=0):
         voltage_capacitance_model=None, use_sparse=False, num_charge_states=32, charge_state_batch_size=1000,
         charge_carrier="electrons", device=device, **kw)
     if "vc" in d and d["vc"].any():                      # qarray_base_class.py:846-852
-        from qarray_latched.DotArrays.voltage_dependent_capacitance import create_linear_capacitance_model
-        model.voltage_capacitance_model = create_linear_capacitance_model(
-            cdd_0=model.cdd_full, cgd_0=model.cgd_full, alpha=float(d["vc"][0]), beta=float(d["vc"][1]))
+        from qarray_latched.DotArrays import voltage_dependent_capacitance as vdc
+        kind = int(d["vc_kind"]) if "vc_kind" in d else 0
+        a, b = float(d["vc"][0]), float(d["vc"][1])
+        if kind == 1:
+            model.voltage_capacitance_model = vdc.create_quadratic_capacitance_model(
+                cdd_0=model.cdd_full, cgd_0=model.cgd_full, gamma=a, beta=b)
+        elif kind == 2:
+            model.voltage_capacitance_model = vdc.create_sigmoid_capacitance_model(
+                cdd_0=model.cdd_full, cgd_0=model.cgd_full, v_char=float(d["vc_vchar"]), delta=a, beta=b)
+        else:
+            model.voltage_capacitance_model = vdc.create_linear_capacitance_model(
+                cdd_0=model.cdd_full, cgd_0=model.cgd_full, alpha=a, beta=b)
     return model
 
 

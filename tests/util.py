@@ -24,7 +24,8 @@ def oracle_model(mb, e: int, flags: int = 0):
         pink_amp=float(p["pink_amp"]) if (flags & FLAG_PINK) and "pink_amp" in (p.dtype.names or ()) else 0.0,
         n_gate=mb.n_gate, cbg=None if mb.cbg is None else mb.cbg[e], tc_base=float(p["tc_base"]),
         alpha=p["alpha"].copy(), num_charge_states=mb.num_charge_states,
-        charge_state_batch_size=mb.charge_state_batch_size, vc_alpha=float(p["vc_alpha"]), vc_beta=float(p["vc_beta"]))
+        charge_state_batch_size=mb.charge_state_batch_size, vc_alpha=float(p["vc_alpha"]), vc_beta=float(p["vc_beta"]),
+        vc_kind=int(p["vc_kind"]), vc_vchar=float(p["vc_vchar"]) if float(p["vc_vchar"]) > 0 else 1.0)
 
 
 def oracle_scan(rec, n_volt: int, flags: int = 0):
@@ -70,14 +71,19 @@ def compare_charges(n_gpu, n_ref, margin, tie_tol=1e-9, max_tie_frac=0.005):
 
 
 def _params_from_bytes(raw):
-    """Fixture bytes -> current PARAMS_DTYPE (fixtures made before ABI 2 lack the vc_alpha / vc_beta fields)."""
+    """Fixture bytes -> current PARAMS_DTYPE.  Older fixtures hold older, shorter records: 712 bytes before ABI 2 (no
+    vc_alpha / vc_beta), 728 bytes in ABI 2 (8 reserved bytes where pink_amp is now; no vc_vchar / vc_kind)."""
     from qdsim import PARAMS_DTYPE
     raw = np.ascontiguousarray(raw)
     if raw.size % PARAMS_DTYPE.itemsize == 0:
         return raw.view(PARAMS_DTYPE).copy()
-    legacy = np.dtype([(n, PARAMS_DTYPE.fields[n][0]) for n in PARAMS_DTYPE.names if n not in ("vc_alpha", "vc_beta")],
-                      align=True)                      # (the trailing 8 bytes were `reserved`, now `pink_amp`: zero either way)
-    assert legacy.itemsize == 712 and raw.size % 712 == 0, (legacy.itemsize, raw.size)
+    new_tail = ("vc_vchar", "vc_kind", "reserved0")
+    abi2 = np.dtype([(n, PARAMS_DTYPE.fields[n][0]) for n in PARAMS_DTYPE.names if n not in new_tail], align=True)
+    abi1 = np.dtype([(n, PARAMS_DTYPE.fields[n][0]) for n in PARAMS_DTYPE.names
+                     if n not in new_tail + ("vc_alpha", "vc_beta")], align=True)
+    assert abi2.itemsize == 728 and abi1.itemsize == 712, (abi2.itemsize, abi1.itemsize)
+    legacy = abi2 if raw.size % 728 == 0 else abi1
+    assert raw.size % legacy.itemsize == 0, raw.size
     old = raw.view(legacy)
     out = np.zeros(old.shape, dtype=PARAMS_DTYPE)
     for n in legacy.names:
