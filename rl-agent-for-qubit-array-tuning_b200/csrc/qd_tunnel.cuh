@@ -1532,12 +1532,14 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
         double pp = 1.0, pc = qi[c_lo] - x;
         bool below = !(pc > 0.0);                  // some eigenvalue lies at or below x
         int i = c_lo + 1;
+        // whole groups of 8 steps, fully unrolled (immediate-offset shared-memory loads), then the remainder
 #pragma unroll 1
-        while (i <= c_hi) {
-          const int i1 = min(i + 8, c_hi + 1);
-#pragma unroll 1
-          for (; i < i1; ++i) {
-            const double pn = fma(qi[i] - x, pc, -e2[i - 1] * pp);
+        for (; i + 7 <= c_hi; i += 8) {
+          const double* __restrict__ q8 = qi + i;
+          const double* __restrict__ e8 = e2 + i - 1;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const double pn = fma(q8[u] - x, pc, -e8[u] * pp);
             below |= !(pn > 0.0);
             pp = pc;
             pc = pn;
@@ -1545,6 +1547,13 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
           const double ap = fabs(pc);
           if (ap < 1e-150) { pc *= 1e150; pp *= 1e150; }      // (irrelevant once `below` is set)
           else if (ap > 1e150) { pc *= 1e-150; pp *= 1e-150; }
+        }
+#pragma unroll 1
+        for (; i <= c_hi; ++i) {
+          const double pn = fma(qi[i] - x, pc, -e2[i - 1] * pp);
+          below |= !(pn > 0.0);
+          pp = pc;
+          pc = pn;
         }
         const unsigned mm = __ballot_sync(0xffffffffu, below);
         const int j = mm ? __ffs(mm) - 1 : 32;
