@@ -47,18 +47,30 @@ __device__ __forceinline__ void hist_add(unsigned* hist, uint32_t b, bool on) {
 }
 
 // The production kernel: one CTA of 1024 threads per env, the env's image held in REGISTERS (up to 32 values per thread,
-// i.e. 32768 pixels per env: 8 dots x 64 x 64 = 28672), so HBM sees one 4-byte read and one typed write per pixel and the
-// radix passes touch no memory but their histograms.  Passes whose byte is the same for every pixel of the env (sign and
-// exponent of a sensor image, mostly) are skipped outright: (kmin >> shift) == (kmax >> shift).
+// i.e. 32768 pixels per env: 8 dots x 64 x 64 = 28672), so HBM sees one 4-byte read and one typed write per pixel.
+//
+// The two percentiles of the reference (0.5 % and 99.5 %) are EXTREME order statistics: ranks k, k+1 with k ~ 143 from the
+// bottom and from the top of 28672 values.  So instead of histogramming every pixel, the kernel
+//   (1) takes each thread's minimum and maximum; the (k_lo+2)-th smallest of the 1024 thread minima, T_lo, is an upper bound
+//       of the value of rank k_lo+1 (the minima alone are k_lo+2 values <= T_lo); likewise T_hi from the maxima.  Both come
+//       from one 4-pass radix select over ONE value per thread (passes whose byte is common to all values are skipped);
+//   (2) gathers the pixels <= T_lo and >= T_hi into two short shared-memory lists (a few hundred entries: T_lo sits near the
+//       k/1024 quantile of minima-of-28, i.e. near the 0.5 % quantile of the image);
+//   (3) ranks the list entries by counting ((value, position) order, so ties are exact) and picks ranks k, k+1 from each end.
+// Exact for every input.  Inputs that defeat (2) -- more than 1024 pixels tied at an extreme, percentiles that are not
+// extreme, envs larger than 1024 x 32 -- take the full MSB-first radix select over the registers (FULL below).
 template <typename OUT>
 __global__ void __launch_bounds__(1024) qd_normalise_reg_kernel(const float* __restrict__ z, OUT* __restrict__ out,
                                                                 long long per_env, int n_env, double q_lo, double q_hi,
                                                                 double* __restrict__ stats) {
   constexpr int EPT = 32;
+  constexpr int LCAP = 1024;
   __shared__ unsigned hist[4][256];
   __shared__ uint32_t prefix[4];
   __shared__ long long rank[4];
   __shared__ uint32_t red[2][32];
+  __shared__ uint32_t list_lo[LCAP], list_hi[LCAP];
+  __shared__ unsigned cnt[2];
   const int env = blockIdx.x;
   if (env >= n_env) return;
   const float* __restrict__ src = z + (size_t)env * per_env;
@@ -75,66 +87,156 @@ __global__ void __launch_bounds__(1024) qd_normalise_reg_kernel(const float* __r
       kmax = max(kmax, key[e]);
     }
   }
+  const uint32_t tmin = kmin, tmax = kmax;                 // this thread's own extremes
+  const bool has = tid < per_env;                          // the thread holds at least one pixel
   kmin = __reduce_min_sync(0xffffffffu, kmin);
   kmax = __reduce_max_sync(0xffffffffu, kmax);
   if (lane == 0) { red[0][wid] = kmin; red[1][wid] = kmax; }
+  // numpy 'linear' percentile: virtual index (n-1) q, neighbours floor / floor+1 (clamped), weight = fractional part
   // (explicitly rounded product: contracted into the subtraction below it would differ from NumPy in the last bit of t)
   const double vi_lo = __dmul_rn((double)(per_env - 1), q_lo), vi_hi = __dmul_rn((double)(per_env - 1), q_hi);
   const long long k_lo = (long long)floor(vi_lo), k_hi = (long long)floor(vi_hi);
-  if (tid == 0) {
-    rank[0] = k_lo; rank[1] = min(k_lo + 1, per_env - 1);
-    rank[2] = k_hi; rank[3] = min(k_hi + 1, per_env - 1);
-    prefix[0] = prefix[1] = prefix[2] = prefix[3] = 0u;
-  }
+  const long long r_lo1 = min(k_lo + 1, per_env - 1), r_hi1 = min(k_hi + 1, per_env - 1);
+  const long long M = min(per_env, (long long)1024);        // threads that hold pixels
+  // extreme-rank path: enough thread minima / maxima to bound the wanted ranks
+  bool fast = (k_lo + 2 <= M) && (per_env - k_hi <= M) && per_env <= (long long)EPT * 1024;
+  if (tid == 0) { cnt[0] = 0u; cnt[1] = 0u; }
   __syncthreads();
   kmin = __reduce_min_sync(0xffffffffu, red[0][lane]);
   kmax = __reduce_max_sync(0xffffffffu, red[1][lane]);
-  for (int pass = 0; pass < 4; ++pass) {
-    const int shift = 24 - 8 * pass;
-    if ((kmin >> shift) == (kmax >> shift)) {          // every pixel shares this byte (and all above): nothing to select
-      __syncthreads();
-      if (tid < 4) prefix[tid] |= ((kmin >> shift) & 0xffu) << shift;
-      __syncthreads();
-      continue;
-    }
-    for (int i = tid; i < 4 * 256; i += 1024) (&hist[0][0])[i] = 0u;
+
+  if (fast) {
+    // ---- (1) T_lo = ascending rank k_lo+1 of the thread minima, T_hi = ascending rank M - (n - k_hi) of the maxima ----
+    if (tid == 0) { rank[0] = k_lo + 1; rank[1] = M - (per_env - k_hi); prefix[0] = prefix[1] = 0u; }
     __syncthreads();
-    const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
-    const uint32_t p0 = prefix[0], p1 = prefix[1], p2 = prefix[2], p3 = prefix[3];
-    const bool d1 = p1 != p0, d2 = p2 != p0 && p2 != p1, d3 = p3 != p0 && p3 != p1 && p3 != p2;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      if ((kmin >> shift) == (kmax >> shift)) {            // every pixel shares this byte and all above it
+        __syncthreads();
+        if (tid < 2) prefix[tid] |= ((kmin >> shift) & 0xffu) << shift;
+        __syncthreads();
+        continue;
+      }
+      for (int i = tid; i < 2 * 256; i += 1024) (&hist[0][0])[i] = 0u;
+      __syncthreads();
+      const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
+      const uint32_t p0 = prefix[0], p1 = prefix[1];
+      hist_add(hist[0], (tmin >> shift) & 0xffu, has && (tmin & hi_mask) == p0);
+      hist_add(hist[1], (tmax >> shift) & 0xffu, has && (tmax & hi_mask) == p1);
+      __syncthreads();
+      if (tid < 2) {
+        long long r = rank[tid];
+        int bb = 0;
+        for (; bb < 255; ++bb) {
+          const unsigned c = hist[tid][bb];
+          if (r < (long long)c) break;
+          r -= c;
+        }
+        rank[tid] = r;
+        prefix[tid] |= (uint32_t)bb << shift;
+      }
+      __syncthreads();
+    }
+    const uint32_t T_lo = prefix[0], T_hi = prefix[1];
+    // ---- (2) gather the pixels at or beyond the two thresholds ----
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
-      const long long i = (long long)e * 1024 + tid;
-      if ((long long)e * 1024 >= per_env) break;       // (uniform over the CTA)
-      const bool in = i < per_env;
-      const uint32_t k = key[e];
-      const uint32_t b = (k >> shift) & 0xffu, top = k & hi_mask;
-      hist_add(hist[0], b, in && top == p0);
-      if (d1) hist_add(hist[1], b, in && top == p1);
-      if (d2) hist_add(hist[2], b, in && top == p2);
-      if (d3) hist_add(hist[3], b, in && top == p3);
-    }
-    __syncthreads();
-    if (tid < 256) {
-      const int b = tid;
-      if (!d1) hist[1][b] = hist[0][b];
-      if (!d2) hist[2][b] = (p2 == p0) ? hist[0][b] : hist[1][b];
-      if (!d3) hist[3][b] = (p3 == p0) ? hist[0][b] : (p3 == p1) ? hist[1][b] : hist[2][b];
-    }
-    __syncthreads();
-    if (tid < 4) {
-      const int t = tid;
-      long long r = rank[t];
-      int b = 0;
-      for (; b < 255; ++b) {
-        const unsigned c = hist[t][b];
-        if (r < (long long)c) break;
-        r -= c;
+      if ((long long)e * 1024 >= per_env) break;           // (uniform over the CTA)
+      const bool in = (long long)e * 1024 + tid < per_env;
+      const bool lo = in && key[e] <= T_lo, hi = in && key[e] >= T_hi;
+      const unsigned ml = __ballot_sync(0xffffffffu, lo), mh = __ballot_sync(0xffffffffu, hi);
+      if (ml) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&cnt[0], (unsigned)__popc(ml));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned at = base + __popc(ml & ((1u << lane) - 1u));
+        if (lo && at < LCAP) list_lo[at] = key[e];
       }
-      rank[t] = r;
-      prefix[t] |= (uint32_t)b << shift;
+      if (mh) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&cnt[1], (unsigned)__popc(mh));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned at = base + __popc(mh & ((1u << lane) - 1u));
+        if (hi && at < LCAP) list_hi[at] = key[e];
+      }
     }
     __syncthreads();
+    const unsigned L0 = cnt[0], L1 = cnt[1];
+    fast = L0 <= (unsigned)LCAP && L1 <= (unsigned)LCAP;   // (uniform) otherwise: massive ties at an extreme -> FULL
+    if (fast) {
+      // ---- (3) rank by counting.  The gather order is arbitrary, but ties hold EQUAL values: any consistent tie-break
+      // (here: list position) yields the same value at every rank ----
+      if (tid < (int)L0) {
+        const uint32_t v = list_lo[tid];
+        unsigned r = 0;
+        for (unsigned j = 0; j < L0; ++j) { const uint32_t w = list_lo[j]; r += (w < v || (w == v && j < (unsigned)tid)) ? 1u : 0u; }
+        if ((long long)r == k_lo) prefix[0] = v;
+        if ((long long)r == r_lo1) prefix[1] = v;
+      }
+      if (tid < (int)L1) {
+        const uint32_t v = list_hi[tid];
+        unsigned r = 0;                                     // rank from the TOP
+        for (unsigned j = 0; j < L1; ++j) { const uint32_t w = list_hi[j]; r += (w > v || (w == v && j < (unsigned)tid)) ? 1u : 0u; }
+        if ((long long)r == per_env - 1 - k_hi) prefix[2] = v;
+        if ((long long)r == per_env - 1 - r_hi1) prefix[3] = v;
+      }
+    }
+    __syncthreads();
+  }
+  if (!fast) {
+    // ---- FULL: MSB-first 8-bit radix select of the four ranks over all pixels (in registers) ----
+    if (tid == 0) {
+      rank[0] = k_lo; rank[1] = r_lo1; rank[2] = k_hi; rank[3] = r_hi1;
+      prefix[0] = prefix[1] = prefix[2] = prefix[3] = 0u;
+    }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      if ((kmin >> shift) == (kmax >> shift)) {          // every pixel shares this byte (and all above): nothing to select
+        __syncthreads();
+        if (tid < 4) prefix[tid] |= ((kmin >> shift) & 0xffu) << shift;
+        __syncthreads();
+        continue;
+      }
+      for (int i = tid; i < 4 * 256; i += 1024) (&hist[0][0])[i] = 0u;
+      __syncthreads();
+      const uint32_t hi_mask = (pass == 0) ? 0u : (0xffffffffu << (shift + 8));
+      const uint32_t p0 = prefix[0], p1 = prefix[1], p2 = prefix[2], p3 = prefix[3];
+      const bool d1 = p1 != p0, d2 = p2 != p0 && p2 != p1, d3 = p3 != p0 && p3 != p1 && p3 != p2;
+#pragma unroll
+      for (int e = 0; e < EPT; ++e) {
+        const long long i = (long long)e * 1024 + tid;
+        if ((long long)e * 1024 >= per_env) break;       // (uniform over the CTA)
+        const bool in = i < per_env;
+        const uint32_t k = key[e];
+        const uint32_t b = (k >> shift) & 0xffu, top = k & hi_mask;
+        hist_add(hist[0], b, in && top == p0);
+        if (d1) hist_add(hist[1], b, in && top == p1);
+        if (d2) hist_add(hist[2], b, in && top == p2);
+        if (d3) hist_add(hist[3], b, in && top == p3);
+      }
+      __syncthreads();
+      if (tid < 256) {
+        const int b = tid;
+        if (!d1) hist[1][b] = hist[0][b];
+        if (!d2) hist[2][b] = (p2 == p0) ? hist[0][b] : hist[1][b];
+        if (!d3) hist[3][b] = (p3 == p0) ? hist[0][b] : (p3 == p1) ? hist[1][b] : hist[2][b];
+      }
+      __syncthreads();
+      if (tid < 4) {
+        const int t = tid;
+        long long r = rank[t];
+        int b = 0;
+        for (; b < 255; ++b) {
+          const unsigned c = hist[t][b];
+          if (r < (long long)c) break;
+          r -= c;
+        }
+        rank[t] = r;
+        prefix[t] |= (uint32_t)b << shift;
+      }
+      __syncthreads();
+    }
   }
   const double a_lo = (double)key_f32(prefix[0]), b_lo = (double)key_f32(prefix[1]);
   const double a_hi = (double)key_f32(prefix[2]), b_hi = (double)key_f32(prefix[3]);

@@ -187,14 +187,19 @@ class Engine:
     def scan_launch(self, z_out, n_out=None, n_type: int = N_NONE, flags: int = 0, stream=None):
         self._check(self._lib.qd_scan_launch(self._ctx, _ptr(z_out), _ptr(n_out), n_type, flags, self._stream(stream)))
 
-    def scan_open_host(self, scans: np.ndarray, n_type: int = N_U8, flags: int = 0, want_z: bool = True,
+    def scan_open_host(self, scans: np.ndarray, n_type: int | None = None, flags: int = 0, want_z: bool = True,
                        z_out: np.ndarray | None = None, n_out: np.ndarray | None = None):
         """Synchronous launch returning host arrays ``(z float32 [pixels], n [pixels, N] or None)``.
+
+        ``n_type`` defaults to what the model produces: uint8 for a hard argmin, float64 for non-integer occupations
+        (tunnel-coupled models, ``FLAG_THERMAL``) -- the library refuses a uint8 charge map there instead of truncating.
 
         Large batches are pipelined inside the library (compute of one chunk overlaps the PCIe copy of the previous
         one); pass pinned ``z_out`` / ``n_out`` (e.g. ``torch.empty(..., pin_memory=True).numpy()``) for full copy speed.
         """
         assert scans.dtype == SCAN_DTYPE and scans.flags.c_contiguous
+        if n_type is None:
+            n_type = N_F64 if (self.models.algorithm.lower() == "tunnel" or flags & FLAG_THERMAL) else N_U8
         pixels = int((scans["pix_offset"] + scans["nx"].astype(np.int64) * scans["ny"]).max())
         z = (z_out if z_out is not None else np.empty(pixels, dtype=np.float32)) if want_z else None
         n = None
