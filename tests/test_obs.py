@@ -75,6 +75,54 @@ def test_percentile_normalisation_is_bit_exact_vs_numpy(engine, per_env, n_env):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("case", ["ties_low_fit", "ties_low_overflow", "ties_high_overflow", "median", "ragged_1500",
+                                  "two_values", "negative_and_zero", "sensor_like", "exactly_1024", "k_plus_2_equals_m"])
+def test_percentile_kernel_paths_are_bit_exact(engine, case):
+    """The extreme-rank path of qd_normalise_reg_kernel (thread minima / maxima -> short lists -> rank by counting) and its
+    fallbacks (more than 1024 pixels tied at an extreme, non-extreme percentiles), on inputs built to hit each of them:
+    statistics and fp32 images bit for bit against np.percentile + the reference's expression (env.py:471-509)."""
+    import torch
+    rng = np.random.default_rng(sum(map(ord, case)))
+    q_low, q_high, per_env, n_env = 0.5, 99.5, 7 * 64 * 64, 3
+    if case == "ragged_1500":
+        per_env = 1500
+    elif case == "exactly_1024":
+        per_env = 1024
+    elif case == "k_plus_2_equals_m":
+        per_env = 700                                             # q = 0.5 / 99.5 -> k_lo = 3: far inside; then stress q
+        q_low, q_high = 40.0, 60.0                                # k_lo + 2 = 281 <= 700 = M: still the extreme-rank path
+    z = rng.normal(0.6, 0.3, (n_env, per_env)).astype(np.float32)
+    if case == "ties_low_fit":
+        z[0, rng.choice(per_env, 600, replace=False)] = z[0].min() - 1.0          # 600 pixels tied at the minimum
+        z[1, rng.choice(per_env, 900, replace=False)] = z[1].max() + 1.0          # 900 tied at the maximum
+    elif case == "ties_low_overflow":
+        z[0, rng.choice(per_env, 5000, replace=False)] = z[0].min() - 1.0         # list overflow -> full radix select
+    elif case == "ties_high_overflow":
+        z[1, rng.choice(per_env, 9000, replace=False)] = z[1].max() + 0.5
+    elif case == "median":
+        q_low, q_high = 50.0, 50.0                                                # not extreme: full radix select
+    elif case == "two_values":
+        z[:] = np.where(rng.random(z.shape) < 0.5, np.float32(0.1), np.float32(0.9))
+    elif case == "negative_and_zero":
+        z[0] = rng.normal(0.0, 1e-3, per_env).astype(np.float32)
+        z[0, ::7] = 0.0
+        z[1, ::5] = -0.0
+    elif case == "sensor_like":                                                   # plateaus + tiny noise, like a real image
+        z = (np.float32(0.0305) + np.float32(1e-4) * rng.standard_normal((n_env, per_env))).astype(np.float32)
+        z[:, : per_env // 3] += np.float32(0.4)
+    z_dev = torch.from_numpy(np.ascontiguousarray(z)).cuda()
+    stats = torch.empty((n_env, 2), dtype=torch.float64, device="cuda")
+    out = engine.normalise_obs(z_dev.clone(), per_env=per_env, n_env=n_env, q_low=q_low, q_high=q_high, stats=stats)
+    torch.cuda.synchronize()
+    for e in range(n_env):
+        img = z[e].astype(np.float64)
+        p_low, p_high = np.percentile(img, q_low), np.percentile(img, q_high)
+        want = np.clip((img - p_low) / (p_high - p_low), 0, 1) if p_high > p_low else np.zeros_like(img)
+        assert stats[e, 0].item() == p_low and stats[e, 1].item() == p_high, (case, e)
+        assert np.array_equal(out[e].cpu().numpy(), want.astype(np.float32)), (case, e)
+
+
+@pytest.mark.gpu
 def test_observe_batch_end_to_end(engine):
     """obs_scans -> scan kernel -> normalisation, against the oracle + np.percentile env by env."""
     import torch
