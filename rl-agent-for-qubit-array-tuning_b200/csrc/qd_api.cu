@@ -14,6 +14,7 @@
 
 #include "qd_kernels.cuh"
 #include "qd_tunnel.cuh"
+#include "qd_tunnel_noda.cuh"
 #include "qd_normalise.cuh"
 
 static_assert(sizeof(qd_scan) == 480, "qd_scan must be 480 bytes (multiple of 16 for the TMA bulk copy)");
@@ -146,6 +147,7 @@ kernel_fn pick_n(int n) {
 QD_PICK_N(pick_tunnel_relax, qd_tunnel_relax_kernel)
 QD_PICK_N(pick_tunnel_select, qd_tunnel_select_kernel)
 QD_PICK_N(pick_tunnel_eigen, qd_tunnel_eigen_kernel)
+QD_PICK_N(pick_tunnel_eigen2, qd_tunnel_eigen2_kernel)
 
 kernel_fn pick_fast(int n) {
   switch (n) {
@@ -277,7 +279,7 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
     g.n_out = nullptr; g.nbar = ctx->d_nbar; g.n_scan = n_scan; g.n_type = QD_N_NONE; g.flags = flags;
     g.status = ctx->d_status;
     g.topt = 7;
-    if (const char* e = getenv("QDSIM_TUNNEL_OPT")) g.topt = atoi(e);
+    if (const char* e = getenv("QDSIM_TUNNEL_OPT")) g.topt = atoi(e) & 7;
     const long long max_pix = ctx->up_max_pix;
     const char* mono_e = getenv("QDSIM_TUNNEL_MONO");
     const bool mono = mono_e && mono_e[0] == '1';
@@ -352,8 +354,26 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
           ks<<<(unsigned)ggrid, gw * 32, smem, stream>>>(sa);
           QD_CUDA(ctx, cudaGetLastError());
         }
-        {
+        // E: the Noda-iteration kernel first (QDSIM_EIGEN=householder skips it); what it could not do (sectors of more
+        // than 16 states, no convergence) is marked with a NaN and redone by the Householder kernel in fix-up mode
+        const char* eig_e = getenv("QDSIM_EIGEN");
+        const bool householder_only = eig_e && eig_e[0] == 'h';
+        const bool no_fixup = eig_e && eig_e[0] == 'n';          // (measurement only: leaves the NaN marks in place)
+        if (!householder_only) {
+          kernel_fn ke2 = pick_tunnel_eigen2(N);
           qd::KArgs ea = g;
+          ea.slot_bytes = qd::qd_tunnel_eigen2_slot_bytes(ctx->L);
+          const size_t smem = (size_t)ea.slot_bytes * gw;
+          rc = configure_kernel(ctx, (const void*)ke2, smem);
+          if (rc) return rc;
+          ke2<<<(unsigned)ggrid, gw * 32, smem, stream>>>(ea);
+          QD_CUDA(ctx, cudaGetLastError());
+          ctx->launches += 1;
+        }
+        if (!no_fixup) {
+          qd::KArgs ea = g;
+          if (!householder_only) ea.topt |= 8;
+          else ea.topt &= ~8;
           ea.slot_bytes = qd::qd_tunnel_eigen_slot_bytes(ctx->L);
           const size_t smem = (size_t)ea.slot_bytes * gw;
           rc = configure_kernel(ctx, (const void*)ke, smem);

@@ -1323,6 +1323,8 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
     for (long long pix = p_begin; pix < p_end; ++pix) {
       const int iy = (int)(pix / nx), ix = (int)(pix - (long long)iy * nx);
       double nbar[N];
+      // fix-up mode (topt bit 3): only the pixels qd_tunnel_eigen2_kernel marked with a NaN are (re)done here
+      if ((a.topt & 8) && a.nbar[(pix0 + pix) * N] == a.nbar[(pix0 + pix) * N]) continue;
       if (!replace) {
         uint64_t key = a.tkeys[((size_t)scan_id * a.tstride + pix) * 32 + lane];
         // ---------------- voltages, potentials, tunnel couplings ----------------
