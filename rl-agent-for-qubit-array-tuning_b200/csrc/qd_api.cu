@@ -362,6 +362,10 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
         if (!householder_only) {
           kernel_fn ke2 = pick_tunnel_eigen2(N);
           qd::KArgs ea = g;
+          ea.e2_kappa = 4.0f; ea.e2_qsafe = 4.0f; ea.e2_tol = 2e-10f;
+          if (const char* e = getenv("QDSIM_E2_KAPPA")) ea.e2_kappa = (float)atof(e);
+          if (const char* e = getenv("QDSIM_E2_QSAFE")) ea.e2_qsafe = (float)atof(e);
+          if (const char* e = getenv("QDSIM_E2_TOL")) ea.e2_tol = (float)atof(e);
           ea.slot_bytes = qd::qd_tunnel_eigen2_slot_bytes(ctx->L);
           const size_t smem = (size_t)ea.slot_bytes * gw;
           rc = configure_kernel(ctx, (const void*)ke2, smem);

@@ -42,6 +42,7 @@ struct KArgs {
   unsigned long long* tkeys;           // [slots][32]  the 32 kept basis states, 8 bits per dot
   long long tstride;                   // pixels per scan slot (largest scan of the upload)
   int topt;                            // tunnel path: optimisation switches (QDSIM_TUNNEL_OPT, default all on; A/B and bisection)
+  float e2_kappa, e2_qsafe, e2_tol;    // qd_tunnel_eigen2_kernel: shift aggressiveness, contraction safety factor, stopping tolerance
   // single-scan fast path (one do2d_open): the descriptor travels in the kernel parameters instead of through a
   // host-to-device copy; `scans` is then unused
   int use_one;

@@ -1300,6 +1300,13 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
     const int scan_id = (int)(item / a.items_per_scan);
     const int part = (int)(item - (long long)scan_id * a.items_per_scan);
     const qd_scan* gscan = a.scans + scan_id;
+    if (a.topt & 8) {
+      // fix-up mode: qd_tunnel_eigen2_kernel left an item-level mark in the floor scratch of the item's first pixel (same
+      // item geometry in both launches); an item without a marked pixel is skipped before anything is staged
+      const long long pb = (long long)part * a.rows_per_item;
+      if (pb >= (long long)gscan->nx * gscan->ny) continue;
+      if (a.tfloor[((size_t)scan_id * a.tstride + pb) * 8] != 0xff) continue;
+    }
     if (lane == 0) {
       const int env = gscan->env_id;
       fence_proxy_async();

@@ -29,7 +29,8 @@ constexpr int QD_E2_LS = 17;                         // row stride of the sector
 constexpr int QD_E2_CB = 48;                         // one pivot-column buffer (lane + 15 stays inside)
 // H17 | Lm (vv[16] gs[8] ts[8] alias its head: they are dead before the first factorisation) | colbuf[2][48] (the
 // start vector of the first mat-vec and the sort permutation alias it) | hash keys[64] | hash x[64]
-constexpr int QD_E2_WORK = 2 * 32 * QD_E2_LS + 2 * QD_E2_CB + 128;
+constexpr int QD_E2_PAD = 32;                        // see e2_factor_sm
+constexpr int QD_E2_WORK = 2 * 32 * QD_E2_LS + 2 * QD_E2_CB + 128 + QD_E2_PAD;
 constexpr int QD_E2_MAXIT = 12;
 
 __host__ __device__ inline int qd_tunnel_eigen2_slot_bytes(const qd_layout& L) {
@@ -200,29 +201,31 @@ __device__ __forceinline__ double e2_solve(const double* __restrict__ Lm, int la
 // ---- compact alternative (QD_E2_SMEM_FACTOR): the factorisation in place in shared memory, rolled loops.  ~15 % more
 // instructions per factorisation than the register form above, a tenth of its code.  W[i][k] (i > k) keeps
 // l_ik d_k; the substitutions scale by 1 / d_k on the fly.
-__device__ __forceinline__ bool e2_factor_sm(const double* __restrict__ hrow, double* W, int lane, int s0, int ri, int m, double d,
+__device__ __forceinline__ bool e2_factor_sm(const double* __restrict__ hrow, double* W, int lane, int s0, int ri, double d,
                                              double pfloor, double& dinv, int mact) {
+  // Loops run to the warp-uniform mact without clamps: a sector shorter than mact reads rows past its end (other
+  // sectors' rows, or -- past lane 31 -- the buffers behind W and the QD_E2_PAD doubles that follow them) into columns at
+  // or beyond its own size, which nothing reads back.
   double* wrow = W + lane * QD_E2_LS;
-  const int mm = min(m, mact);                     // own sector's columns only (a sector larger than mact is not in play)
 #pragma unroll 4
-  for (int c = 0; c < mm; ++c) wrow[c] = hrow[c];
+  for (int c = 0; c < mact; ++c) wrow[c] = hrow[c];
   wrow[min(ri, 15)] = d;
   bool fail = false;
-  const double* __restrict__ diag = W + s0 * QD_E2_LS;      // + k * (LS + 1): the sector's k-th pivot
+  const double* __restrict__ diag = W + s0 * (QD_E2_LS) ;
 #pragma unroll 1
   for (int k = 0; k < mact; ++k) {
     __syncwarp();
-    double piv = diag[min(k, m - 1) * (QD_E2_LS + 1)];
+    double piv = diag[k * (QD_E2_LS + 1)];
     const bool ok = piv > pfloor;
     if (ri == k) fail = !ok;
     piv = ok ? piv : pfloor;
     const double inv = rcp_nr(piv);
     if (ri == k) dinv = inv;
     const double l = (ri > k) ? wrow[k] * inv : 0.0;
-    const double* __restrict__ tp = W + (s0 + k + 1) * QD_E2_LS + k;      // column k, rows k+1.. of the sector
+    const double* __restrict__ tp = diag + (k + 1) * QD_E2_LS + k;         // column k, rows k+1.. of the sector
     double* __restrict__ wp = wrow + k + 1;
 #pragma unroll 4
-    for (int c = k + 1; c < mm; ++c, tp += QD_E2_LS, ++wp) *wp = fma(-l, *tp, *wp);
+    for (int c = k + 1; c < mact; ++c, tp += QD_E2_LS, ++wp) *wp = fma(-l, *tp, *wp);
   }
   __syncwarp();
   return fail;
@@ -230,18 +233,19 @@ __device__ __forceinline__ bool e2_factor_sm(const double* __restrict__ hrow, do
 __device__ __forceinline__ double e2_solve_sm(const double* __restrict__ W, int lane, int s0, int ri, int m, double dinv, double x,
                                               int mact) {
   const double* __restrict__ wrow = W + lane * QD_E2_LS;
-  const int last = s0 + m - 1;
   double y = x;
 #pragma unroll 4
   for (int k = 0; k + 1 < mact; ++k) {
-    const double zk = shfl_f64(y * dinv, min(s0 + k, last));
-    if (ri > k) y = fma(-wrow[k], zk, y);
+    const double zk = shfl_f64(y * dinv, min(s0 + k, 31));
+    const double w = wrow[k];
+    if (ri > k) y = fma(-w, zk, y);
   }
   const double* __restrict__ wcol = W + s0 * QD_E2_LS + ri;      // + k * LS: W[s0 + k][ri]
 #pragma unroll 4
   for (int k = mact - 1; k >= 1; --k) {
-    const double zk = shfl_f64(y * dinv, min(s0 + k, last));
-    if (ri < k && k < m) y = fma(-wcol[min(k, m - 1) * QD_E2_LS], zk, y);
+    const double zk = shfl_f64(y * dinv, min(s0 + k, 31));
+    const double w = wcol[k * QD_E2_LS];
+    if (ri < k && k < m) y = fma(-w, zk, y);
   }
   return y * dinv;
 }
@@ -277,6 +281,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
   double* colbuf = Lm + 32 * QD_E2_LS;              // [2][48]
   uint64_t* hkey = reinterpret_cast<uint64_t*>(colbuf + 2 * QD_E2_CB);   // [64]
   double* hx = reinterpret_cast<double*>(hkey + 64);                     // [64]
+  if (lane < QD_E2_PAD / 2) { hx[64 + lane] = 0.0; hx[64 + 16 + lane] = 0.0; }
   uint64_t* bar = reinterpret_cast<uint64_t*>(wk + QD_E2_WORK);
   const double* __restrict__ C = rec + L.o_cinv;
 
@@ -316,6 +321,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
     hkey[lane] = ~0ULL;
     hkey[lane + 32] = ~0ULL;
     double gtil = -1.0;
+    bool any_fallback = false;
     __syncwarp();
 
     for (long long pix = p_begin; pix < p_end; ++pix) {
@@ -415,20 +421,33 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
 #pragma unroll 1
         for (int u = 0; u < maxlen; ++u) {
           const int j = min(s0 + u, 31);
-          const uint64_t kj = shfl_u64(key, j);
+          const uint64_t kj = (N <= 4) ? (uint64_t)__shfl_sync(FULL, (unsigned)key, j) : shfl_u64(key, j);
           double val = (j == lane) ? Fm : 0.0;
           // a hop p -> p+1 takes one from byte p and adds one to byte p+1: as 64-bit integers the two packed states
           // differ by exactly 0xFF << 8p (no byte wraps: occupations stay inside 0..255)
-          const long long df = (long long)(kj - key);
-          const uint64_t ad = (uint64_t)(df < 0 ? -df : df);
-          const int tz = __ffsll((long long)ad) - 1;
-          if ((tz & 7) == 0 && (ad >> (tz & 63)) == 0xFFull && u < m) {
-            const unsigned pa = (unsigned)(key >> tz) & 0xffffu;
-            const unsigned a0 = pa & 0xffu, a1 = pa >> 8;
-            // df > 0: the partner has one more in dot p+1 (this state hops p -> p+1), else p+1 -> p
-            const double amp = (df > 0) ? sq_tab[a0] * sq_tab[a1 + 1] : sq_tab[a1] * sq_tab[a0 + 1];
-            val = -ts[tz >> 3] * amp;
-            rowabs -= val;
+          if constexpr (N <= 4) {                     // the packed state fits 32 bits: same test at half the instructions
+            const int df = (int)((unsigned)kj - (unsigned)key);
+            const unsigned ad = (unsigned)(df < 0 ? -df : df);
+            const int tz = __ffs((int)ad) - 1;
+            if ((tz & 7) == 0 && (ad >> (tz & 31)) == 0xFFu && u < m) {
+              const unsigned pa = ((unsigned)key >> tz) & 0xffffu;
+              const unsigned a0 = pa & 0xffu, a1 = pa >> 8;
+              const double amp = (df > 0) ? sq_tab[a0] * sq_tab[a1 + 1] : sq_tab[a1] * sq_tab[a0 + 1];
+              val = -ts[tz >> 3] * amp;
+              rowabs -= val;
+            }
+          } else {
+            const long long df = (long long)(kj - key);
+            const uint64_t ad = (uint64_t)(df < 0 ? -df : df);
+            const int tz = __ffsll((long long)ad) - 1;
+            if ((tz & 7) == 0 && (ad >> (tz & 63)) == 0xFFull && u < m) {
+              const unsigned pa = (unsigned)(key >> tz) & 0xffffu;
+              const unsigned a0 = pa & 0xffu, a1 = pa >> 8;
+              // df > 0: the partner has one more in dot p+1 (this state hops p -> p+1), else p+1 -> p
+              const double amp = (df > 0) ? sq_tab[a0] * sq_tab[a1 + 1] : sq_tab[a1] * sq_tab[a0 + 1];
+              val = -ts[tz >> 3] * amp;
+              rowabs -= val;
+            }
           }
           hrow[u] = (u < m) ? val : 0.0;
         }
@@ -484,7 +503,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
         int nsol = 0;
         if (isg) {
           double eta = 1.5 * (double)sqrtf((float)rr);
-          if (gtil > 0.0) eta = fmin(eta, 4.0 * rr / gtil);
+          if (gtil > 0.0) eta = fmin(eta, (double)a.e2_kappa * rr / gtil);
           eta += 1e-13 * scale;
           sig = fmax(lo, rho0 - eta);
           agg = sig > lo;
@@ -506,7 +525,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
           if (need_fac) {
             if (test && live) sig = U;
 #ifndef QD_E2_REG_FACTOR
-            const bool fl = e2_factor_sm(hrow, Lm, lane, s0, ri, m, Fm - sig, pfloor, dinv, mact);
+            const bool fl = e2_factor_sm(hrow, Lm, lane, s0, ri, Fm - sig, pfloor, dinv, mact);
 #else
             const bool fl = e2_factor(hrow, Lm + lane * QD_E2_LS, colbuf, lane, s0, ri, Fm - sig, pfloor, dinv, mact);
 #endif
@@ -558,8 +577,8 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
               if (nsol == 1) {
                 if (agg) {
                   if (gtil > 0.0) {
-                    const float q = fminf(1.0f, (float)(4.0 * (ub - sig) / gtil));
-                    if (eps * q < 2e-10f || eps < 3e-8f) done = true;
+                    const float q = fminf(1.0f, a.e2_qsafe * (float)((ub - sig) / gtil));
+                    if (eps * q < a.e2_tol || eps < 3e-8f) done = true;
                     else if (q > 0.03f) want_rmin = true;
                   } else if (eps < 3e-8f) {
                     done = true;
@@ -569,7 +588,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
                 }
               } else {
                 const float q = fminf(1.0f, eps / eps_prev);
-                if (eps * q < 2e-10f) done = true;
+                if (eps * q < a.e2_tol) done = true;
                 else if (q > 0.03f) want_rmin = true;
               }
               eps_prev = eps;
@@ -618,6 +637,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
       if (fallback) {
         if (lane == 0) out[0] = __longlong_as_double(0x7ff8000000000000LL);      // redone by the fix-up pass
         gtil = -1.0;
+        any_fallback = true;
       } else {
         const unsigned k32 = (unsigned)key ^ (unsigned)(key >> 32);
         int h = (int)((k32 * 0x9E3779B1u) >> 26);
@@ -633,6 +653,8 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
       }
       __syncwarp();
     }
+    // item-level mark for the fix-up pass, in the (by now consumed) floor scratch of the item's first pixel
+    if (lane == 0) a.tfloor[((size_t)scan_id * a.tstride + p_begin) * 8] = any_fallback ? 0xff : 0;
     __syncwarp();
   }
 }
