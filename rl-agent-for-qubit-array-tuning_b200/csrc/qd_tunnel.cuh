@@ -1199,22 +1199,32 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
           beta_b = 2.0 * (c[0] - fma(c[1], Mi[9], fma(c[2], Mi[10], c[3] * Mi[11])));
           gamma_b = Mi[12];
         }
+        // every candidate of inner iteration i has the leading low digit i >> 1: the iteration is skipped when even the
+        // continuous minimum over the other three low digits lies above the current 32nd-best energy (tau only falls)
+        double bnd4[4] = {-INF, -INF, -INF, -INF};
+        if (NLO == 4 && (a.topt & 1)) {
+#pragma unroll
+          for (int dg = 0; dg < 4; ++dg) {
+            const double y0 = (double)(dg - 1);
+            const double bnd = fma(y0, fma(gamma_b, y0, beta_b), alpha_b);
+            bnd4[dg] = bnd - 1e-12 * (fabs(bnd) + 1.0);
+          }
+        }
 #pragma unroll 1
         for (int ii = 0; ii < LO_IT; ++ii) {
           const int i = (LO_IT >= 4) ? ((ii + LO_IT / 4) & (LO_IT - 1)) : ii;
-          if (NLO == 4 && (a.topt & 1)) {
-            // every candidate of this iteration has the leading low digit i >> 1: skip it when even the continuous minimum
-            // over the other three low digits lies above the current 32nd-best energy
-            const double y0 = (double)((i >> 1) - 1);
-            const double bnd = fma(y0, fma(gamma_b, y0, beta_b), alpha_b);
-            if (bnd - 1e-12 * (fabs(bnd) + 1.0) > tau) continue;
+          if (NLO == 4) {
+            const int dg = i >> 1;
+            const double bnd = (dg == 0) ? bnd4[0] : (dg == 1) ? bnd4[1] : (dg == 2) ? bnd4[2] : bnd4[3];
+            if (bnd > tau) continue;
           }
           const int b = i * 32 + lane;
           const bool ok = (lo_valid >> i) & 1u;
           double e = INF;
           if (ok) e = tunnel_iter_part<NLO>(base_lane + Ql[b], c, i);
           const int cidx = mb * NB_LO + b;
-          unsigned pmk = __ballot_sync(0xffffffffu, ok && lex_less(e, cidx, tau, tau_idx));
+          // cheap superset of lex_less(e, cidx, tau, tau_idx); the exact (energy, index) test is made on every candidate taken
+          unsigned pmk = __ballot_sync(0xffffffffu, ok && !(e > tau));
           while (pmk) {
             const int p = __ffs(pmk) - 1;
             pmk &= pmk - 1u;
