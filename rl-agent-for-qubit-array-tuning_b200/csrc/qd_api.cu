@@ -879,7 +879,14 @@ int qd_scan_open_host(qd_ctx* ctx, int n_scan, const qd_scan* scans, float* z_ou
                 ctx->d_small + zoff, n_type, flags, ctx->s_compute, 0, one ? scans : nullptr);
     if (rc) return rc;
     const auto t1 = clk::now();
-    QD_CUDA(ctx, cudaStreamSynchronize(ctx->s_compute));
+    // a latency-bound call: poll the stream instead of cudaStreamSynchronize (whose wake-up costs microseconds); bounded,
+    // then fall back to the blocking wait
+    {
+      cudaError_t q = cudaErrorNotReady;
+      for (int spin = 0; spin < 200000 && q == cudaErrorNotReady; ++spin) q = cudaStreamQuery(ctx->s_compute);
+      if (q == cudaErrorNotReady) q = cudaStreamSynchronize(ctx->s_compute);
+      QD_CUDA(ctx, q);
+    }
     const auto t2 = clk::now();
     ctx->staged_pending = false;
     if (z_out_host) memcpy(z_out_host, ctx->h_small, zbytes);

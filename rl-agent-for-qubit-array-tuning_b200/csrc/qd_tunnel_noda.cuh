@@ -29,7 +29,7 @@ constexpr int QD_E2_LS = 17;                         // row stride of the sector
 constexpr int QD_E2_CB = 48;                         // one pivot-column buffer (lane + 15 stays inside)
 // H17 | Lm (vv[16] gs[8] ts[8] alias its head: they are dead before the first factorisation) | colbuf[2][48] (the
 // start vector of the first mat-vec and the sort permutation alias it) | hash keys[64] | hash x[64]
-constexpr int QD_E2_PAD = 32;                        // see e2_factor_sm
+constexpr int QD_E2_PAD = 48;                        // see e2_factor_sm
 constexpr int QD_E2_WORK = 2 * 32 * QD_E2_LS + 2 * QD_E2_CB + 128 + QD_E2_PAD;
 constexpr int QD_E2_MAXIT = 12;
 
@@ -224,8 +224,14 @@ __device__ __forceinline__ bool e2_factor_sm(const double* __restrict__ hrow, do
     const double l = (ri > k) ? wrow[k] * inv : 0.0;
     const double* __restrict__ tp = diag + (k + 1) * QD_E2_LS + k;         // column k, rows k+1.. of the sector
     double* __restrict__ wp = wrow + k + 1;
-#pragma unroll 4
-    for (int c = k + 1; c < mact; ++c, tp += QD_E2_LS, ++wp) *wp = fma(-l, *tp, *wp);
+    // two columns per trip and NO remainder code (trip counts are 0..7: remainder handling cost more than the loop); the
+    // odd column past mact is the pad column of the stride-17 rows at worst
+    for (int n2 = (mact - k) >> 1; n2 > 0; --n2, tp += 2 * QD_E2_LS, wp += 2) {
+      const double t0 = tp[0], t1 = tp[QD_E2_LS];
+      const double w0 = wp[0], w1 = wp[1];
+      wp[0] = fma(-l, t0, w0);
+      wp[1] = fma(-l, t1, w1);
+    }
   }
   __syncwarp();
   return fail;
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
   double* colbuf = Lm + 32 * QD_E2_LS;              // [2][48]
   uint64_t* hkey = reinterpret_cast<uint64_t*>(colbuf + 2 * QD_E2_CB);   // [64]
   double* hx = reinterpret_cast<double*>(hkey + 64);                     // [64]
-  if (lane < QD_E2_PAD / 2) { hx[64 + lane] = 0.0; hx[64 + 16 + lane] = 0.0; }
+  for (int i = lane; i < QD_E2_PAD; i += 32) hx[64 + i] = 0.0;
   uint64_t* bar = reinterpret_cast<uint64_t*>(wk + QD_E2_WORK);
   const double* __restrict__ C = rec + L.o_cinv;
 
