@@ -15,6 +15,7 @@
 #include "qd_kernels.cuh"
 #include "qd_tunnel.cuh"
 #include "qd_tunnel_noda.cuh"
+#include "qd_tunnel_enum.cuh"
 #include "qd_normalise.cuh"
 
 static_assert(sizeof(qd_scan) == 480, "qd_scan must be 480 bytes (multiple of 16 for the TMA bulk copy)");
@@ -148,6 +149,16 @@ QD_PICK_N(pick_tunnel_relax, qd_tunnel_relax_kernel)
 QD_PICK_N(pick_tunnel_select, qd_tunnel_select_kernel)
 QD_PICK_N(pick_tunnel_eigen, qd_tunnel_eigen_kernel)
 QD_PICK_N(pick_tunnel_eigen2, qd_tunnel_eigen2_kernel)
+kernel_fn pick_tunnel_select2(int n) {
+  switch (n) {
+    case 4: return qd::qd_tunnel_select2_kernel<4>;
+    case 5: return qd::qd_tunnel_select2_kernel<5>;
+    case 6: return qd::qd_tunnel_select2_kernel<6>;
+    case 7: return qd::qd_tunnel_select2_kernel<7>;
+    case 8: return qd::qd_tunnel_select2_kernel<8>;
+    default: return nullptr;      // fewer than 32 candidates can be valid below four dots: the block walk pads
+  }
+}
 
 kernel_fn pick_fast(int n) {
   switch (n) {
@@ -345,8 +356,23 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
         const int gw = (items < (long long)ctx->sm_count * 4) ? 1 : 4;
         long long ggrid = (items + gw - 1) / gw;
         if (ggrid > 0x7fffffffLL) ggrid = 0x7fffffffLL;
+        // S: the lattice-enumeration kernel first (four dots and more; QDSIM_SELECT=block skips it), then the block walk --
+        // as the fix-up pass over the pixels the enumeration marked, or for everything
+        const char* sel_e = getenv("QDSIM_SELECT");
+        kernel_fn ks2 = (sel_e && sel_e[0] == 'b') ? nullptr : pick_tunnel_select2(N);
+        if (ks2) {
+          qd::KArgs sa = g;
+          sa.slot_bytes = qd::qd_tunnel_select2_slot_bytes(ctx->L);
+          const size_t smem = (size_t)sa.slot_bytes * gw;
+          rc = configure_kernel(ctx, (const void*)ks2, smem);
+          if (rc) return rc;
+          ks2<<<(unsigned)ggrid, gw * 32, smem, stream>>>(sa);
+          QD_CUDA(ctx, cudaGetLastError());
+          ctx->launches += 1;
+        }
         {
           qd::KArgs sa = g;
+          if (ks2) sa.topt |= 16;
           sa.slot_bytes = qd::qd_tunnel_select_slot_bytes(ctx->L);
           const size_t smem = (size_t)sa.slot_bytes * gw;
           rc = configure_kernel(ctx, (const void*)ks, smem);

@@ -934,6 +934,14 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
     const int scan_id = (int)(item / a.items_per_scan);
     const int part = (int)(item - (long long)scan_id * a.items_per_scan);
     const qd_scan* gscan = a.scans + scan_id;
+    if (a.topt & 16) {
+      // fix-up mode: only the pixels qd_tunnel_select2_kernel marked (first key = QD_S2_MARK; item-level mark = a NaN in the
+      // <n> scratch of the item's first pixel) are done here, each from a cold start
+      const long long pb = (long long)part * a.rows_per_item;
+      if (pb >= (long long)gscan->nx * gscan->ny) continue;
+      const double fl = a.nbar[(gscan->pix_offset + pb) * N];
+      if (fl == fl) continue;
+    }
     if (lane == 0) {
       const int env = gscan->env_id;
       fence_proxy_async();
@@ -1042,6 +1050,7 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
     for (long long pix = p_begin; pix < p_end; ++pix) {
       const int iy = (int)(pix / nx), ix = (int)(pix - (long long)iy * nx);
       const size_t tslot = (size_t)scan_id * a.tstride + pix;
+      if ((a.topt & 16) && a.tkeys[tslot * 32] != 0xfffffffffffffffeULL) { have_prev = false; continue; }
       // ---------------- potentials, floor (from the relax kernel), r = f - g, h = C r ----------------
       if (lane < NV) {
         vv[lane] = (a.points == nullptr) ? fma((double)iy, sc->dy[lane], fma((double)ix, sc->dx[lane], sc->v0[lane]))

@@ -17,11 +17,14 @@ import torch  # noqa: E402
 from qdsim import N_F64, Engine, synth  # noqa: E402
 
 
+VAR = "QDSIM_EIGEN"
+
+
 def run(eng, scans, pixels, n_dot, steps, mode):
     if mode:
-        os.environ["QDSIM_EIGEN"] = mode
+        os.environ[VAR] = mode
     else:
-        os.environ.pop("QDSIM_EIGEN", None)
+        os.environ.pop(VAR, None)
     z = torch.empty(pixels, dtype=torch.float32, device="cuda")
     n = torch.empty((pixels, n_dot), dtype=torch.float64, device="cuda")
     st = torch.cuda.current_stream()
@@ -43,7 +46,11 @@ def main():
     ap.add_argument("--cases", default="4:256,8:64")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--res", type=int, default=64)
+    ap.add_argument("--var", default="QDSIM_EIGEN", help="environment switch to A/B (QDSIM_EIGEN or QDSIM_SELECT)")
+    ap.add_argument("--ref", default="householder", help="value of the switch for the reference run (QDSIM_SELECT: block)")
     a = ap.parse_args()
+    global VAR
+    VAR = a.var
     eng = Engine(0)
     for case in a.cases.split(","):
         n_dot, n_env = map(int, case.split(":"))
@@ -52,7 +59,7 @@ def main():
         eng.set_models(mb)
         scans = synth.env_step_scans(mb, dev, res=a.res, seed=99, radial=False)
         pixels = len(scans) * a.res * a.res
-        n_h, ms_h = run(eng, scans, pixels, n_dot, a.steps, "householder")
+        n_h, ms_h = run(eng, scans, pixels, n_dot, a.steps, a.ref)
         n_n, ms_n = run(eng, scans, pixels, n_dot, a.steps, "")
         d = np.abs(n_h - n_n).max(axis=1)
         bad = np.nonzero(~(d < 1e-6))[0]
