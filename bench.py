@@ -282,8 +282,10 @@ def issue_roofline(kernels, pixels_per_s: float, sm_count: int, sm_mhz: float):
 
 
 def tunnel_kernels(n_dot: int):
-    # (the Householder kernel's fix-up pass over the pixels the Noda kernel gave up on, < 0.3 % of them, is not counted)
-    return [f"qd_tunnel_select_kernel<{n_dot}>", f"qd_tunnel_eigen2_kernel<{n_dot}>"]
+    # (the fix-up passes of the block-walk select kernel and of the Householder eigen kernel over the pixels the
+    # enumeration / Noda kernels gave up on, < 0.5 % of them, are not counted)
+    sel = "qd_tunnel_select2_kernel" if n_dot >= 4 else "qd_tunnel_select_kernel"
+    return [f"{sel}<{n_dot}>", f"qd_tunnel_eigen2_kernel<{n_dot}>"]
 
 
 def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_env: int = 512, steps: int = 5,
@@ -326,8 +328,8 @@ def tunnel_path_block(eng, n_dot: int, res: int, flags: int, with_cpu: bool, n_e
     props = torch.cuda.get_device_properties(0)
     blk = {"workload": f"{n_dot}-dot tunnel-coupled array (TunnelCoupledChargeSensed, 32-state basis, barrier voltages), "
                        f"{n_env} envs, {n_dot - 1} scans/env of {res}x{res}, latching + noise",
-           "kernels": f"qd_tunnel_relax_kernel<{n_dot}> + qd_tunnel_select_kernel<{n_dot}> + qd_tunnel_eigen2_kernel<{n_dot}> "
-                      f"(+ qd_tunnel_eigen_kernel<{n_dot}> as the fix-up pass) "
+           "kernels": f"qd_tunnel_relax_kernel<{n_dot}> + qd_tunnel_select2_kernel<{n_dot}> + qd_tunnel_eigen2_kernel<{n_dot}> "
+                      f"(+ qd_tunnel_select_kernel / qd_tunnel_eigen_kernel<{n_dot}> as fix-up passes) "
                       f"+ qd_scan_kernel<{n_dot},tunnel>",
            "value": pixels / (ms * 1e-3), "unit": "pixels/s", "env_steps_per_s": n_env / (ms * 1e-3),
            "ms_per_step": ms, "steps": steps, "warmup": warmup, "gpu_launches": int(launches),

@@ -58,11 +58,12 @@ def main():
     if os.path.exists(figs):
         os.remove(figs)
     caps = [("fast8", "qd_scan_fast", 58720256, "qd_scan_kernel<8,default>"),
-            ("select8", "qd_tunnel_select", 1835008, "qd_tunnel_select_kernel<8>"),
+            ("select8", "qd_tunnel_select2", 1835008, "qd_tunnel_select2_kernel<8>"),
             ("eigen8", "qd_tunnel_eigen2", 1835008, "qd_tunnel_eigen2_kernel<8>"),
-            ("select4", "qd_tunnel_select", 3145728, "qd_tunnel_select_kernel<4>"),
+            ("select4", "qd_tunnel_select2", 3145728, "qd_tunnel_select2_kernel<4>"),
             ("eigen4", "qd_tunnel_eigen2", 3145728, "qd_tunnel_eigen2_kernel<4>"),
-            ("hh8", "qd_tunnel_eigen_kernel", 1835008, "qd_tunnel_eigen_kernel<8>")]
+            ("hh8", "qd_tunnel_eigen_kernel", 1835008, "qd_tunnel_eigen_kernel<8>"),
+            ("blk8", "qd_tunnel_select_kernel", 1835008, "qd_tunnel_select_kernel<8>")]
     md = [f"# ncu summary r02 (source hash {sha}; captures of `tools/gpu_job.sh {tag}`)\n",
           "`ncu --set full --clock-control none --import-source on -k regex:<kernel> -c 1`, each after the same command exited 0 "
           "without ncu; raw and source pages exported on the box (`tools/ncu_export.sh`), the 25 MB reports stay there.\n"]
@@ -80,7 +81,8 @@ def main():
         md.append("```")
         src = os.path.join(G, f"prof_{tag}_{name}_src.csv.gz")
         if os.path.exists(src):
-            fname = "qd_kernels.cuh" if name == "fast8" else "qd_tunnel_noda.cuh" if name.startswith("eigen") else "qd_tunnel.cuh"
+            fname = ("qd_kernels.cuh" if name == "fast8" else "qd_tunnel_noda.cuh" if name.startswith("eigen") else
+                     "qd_tunnel_enum.cuh" if name.startswith("select") else "qd_tunnel.cuh")
             top = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), src, "--file", fname, "--top", "14"],
                                  capture_output=True, text=True).stdout
             md.append("\n```\n" + top.strip() + "\n```")

@@ -9,13 +9,14 @@ B="python bench.py --n-env 2048 --steps 2 --warmup 1 --no-path-b --no-cpu-baseli
 $B > $o/${tag}_plainA.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:qd_scan_fast -s 3 -c 1 -o $o/prof_${tag}_fast8 $B > $o/${tag}_ncuA.log 2>&1
 T="python tools/tunnel_time.py --cases 8:64 --steps 1"
 $T > $o/${tag}_plainB.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file $o/${tag}_launches_tunnel.csv $T > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_select -s 2 -c 1 -o $o/prof_${tag}_select8 $T > $o/${tag}_ncuS.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_select2 -s 2 -c 1 -o $o/prof_${tag}_select8 $T > $o/${tag}_ncuS.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_eigen2 -s 2 -c 1 -o $o/prof_${tag}_eigen8 $T > $o/${tag}_ncuE.log 2>&1
 T4="python tools/tunnel_time.py --cases 4:256 --steps 1"
-$T4 > $o/${tag}_plainB4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_select -s 2 -c 1 -o $o/prof_${tag}_select4 $T4 > $o/${tag}_ncuS4.log 2>&1
+$T4 > $o/${tag}_plainB4.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_select2 -s 2 -c 1 -o $o/prof_${tag}_select4 $T4 > $o/${tag}_ncuS4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_eigen2 -s 2 -c 1 -o $o/prof_${tag}_eigen4 $T4 > $o/${tag}_ncuE4.log 2>&1
 QDSIM_EIGEN=householder ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_eigen_kernel -s 2 -c 1 -o $o/prof_${tag}_hh8 $T > $o/${tag}_ncuH.log 2>&1
-tools/ncu_export.sh $o/prof_${tag}_hh8 $o/prof_${tag}_fast8 $o/prof_${tag}_select8 $o/prof_${tag}_eigen8 $o/prof_${tag}_select4 $o/prof_${tag}_eigen4
+QDSIM_SELECT=block ncu --set full --clock-control none --import-source on -k regex:qd_tunnel_select_kernel -s 2 -c 1 -o $o/prof_${tag}_blk8 $T > $o/${tag}_ncuK.log 2>&1
+tools/ncu_export.sh $o/prof_${tag}_blk8 $o/prof_${tag}_hh8 $o/prof_${tag}_fast8 $o/prof_${tag}_select8 $o/prof_${tag}_eigen8 $o/prof_${tag}_select4 $o/prof_${tag}_eigen4
 python tools/sweep.py > $o/${tag}_sweep.json 2> $o/${tag}_sweep.err
 QDSIM_TRACE=1 python tools/latency.py > $o/${tag}_latency.json 2> $o/${tag}_latency.err
 python bench.py --impl reference --steps 3 --warmup 1 > $o/${tag}_bench_reference.json 2>/dev/null

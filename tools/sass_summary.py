@@ -14,7 +14,7 @@ from collections import Counter
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "rl-agent-for-qubit-array-tuning_b200", "csrc", "libqdsim.so")
 HOT = ["qd_scan_fast_kernelILi8E", "qd_scan_fast_kernelILi4E", "qd_scan_kernelILi8ELi0ELb0ELb0E", "qd_scan_kernelILi6ELi2ELb0ELb0E",
-       "qd_scan_kernelILi8ELi3ELb0ELb0E", "qd_tunnel_relax_kernelILi8E", "qd_tunnel_select_kernelILi8E", "qd_tunnel_eigen2_kernelILi8E", "qd_tunnel_eigen_kernelILi8E",
+       "qd_scan_kernelILi8ELi3ELb0ELb0E", "qd_tunnel_relax_kernelILi8E", "qd_tunnel_select_kernelILi8E", "qd_tunnel_select2_kernelILi8E", "qd_tunnel_select2_kernelILi4E", "qd_tunnel_eigen2_kernelILi8E", "qd_tunnel_eigen_kernelILi8E",
        "qd_tunnel_select_kernelILi4E", "qd_tunnel_eigen2_kernelILi4E", "qd_tunnel_eigen_kernelILi4E", "qd_tunnel_gs_kernelILi8E", "qd_normalise_reg_kernelIhE",
        "qd_normalise_reg_kernelIfE", "qd_build_q_kernel"]
 WATCH = ["UBLKCP", "SYNCS", "DFMA", "DADD", "DMUL", "DSETP", "MUFU", "SHFL", "VOTE", "MATCH", "REDUX", "LDS", "STS", "LDG", "STG", "ATOMS",
