@@ -370,14 +370,27 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
           QD_CUDA(ctx, cudaGetLastError());
           ctx->launches += 1;
         }
+        // fix-up launches: items of 8 pixels (no state is carried between marked pixels), so that a stretch of marked pixels
+        // is spread over several warps; col_parts carries the marking kernel's item length to the mark look-up
+        const int fix_ppi = (ppi % 8 == 0) ? 8 : (int)ppi;          // (must divide the marking kernel's item length)
+        const int fix_ips = (int)((max_pix + fix_ppi - 1) / fix_ppi);
+        long long fix_grid = ((long long)nc * fix_ips + gw - 1) / gw;
+        if (fix_grid > 0x7fffffffLL) fix_grid = 0x7fffffffLL;
         {
           qd::KArgs sa = g;
-          if (ks2) sa.topt |= 16;
+          long long sgrid = ggrid;
+          if (ks2) {
+            sa.topt |= 16;
+            sa.col_parts = (int)ppi;
+            sa.rows_per_item = fix_ppi;
+            sa.items_per_scan = fix_ips;
+            sgrid = fix_grid;
+          }
           sa.slot_bytes = qd::qd_tunnel_select_slot_bytes(ctx->L);
           const size_t smem = (size_t)sa.slot_bytes * gw;
           rc = configure_kernel(ctx, (const void*)ks, smem);
           if (rc) return rc;
-          ks<<<(unsigned)ggrid, gw * 32, smem, stream>>>(sa);
+          ks<<<(unsigned)sgrid, gw * 32, smem, stream>>>(sa);
           QD_CUDA(ctx, cudaGetLastError());
         }
         // E: the Noda-iteration kernel first (QDSIM_EIGEN=householder skips it); what it could not do (sectors of more
@@ -402,13 +415,21 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
         }
         if (!no_fixup) {
           qd::KArgs ea = g;
-          if (!householder_only) ea.topt |= 8;
-          else ea.topt &= ~8;
+          long long egrid = ggrid;
+          if (!householder_only) {
+            ea.topt |= 8;
+            ea.col_parts = (int)ppi;
+            ea.rows_per_item = fix_ppi;
+            ea.items_per_scan = fix_ips;
+            egrid = fix_grid;
+          } else {
+            ea.topt &= ~8;
+          }
           ea.slot_bytes = qd::qd_tunnel_eigen_slot_bytes(ctx->L);
           const size_t smem = (size_t)ea.slot_bytes * gw;
           rc = configure_kernel(ctx, (const void*)ke, smem);
           if (rc) return rc;
-          ke<<<(unsigned)ggrid, gw * 32, smem, stream>>>(ea);
+          ke<<<(unsigned)egrid, gw * 32, smem, stream>>>(ea);
           QD_CUDA(ctx, cudaGetLastError());
         }
         ctx->launches += 3;

@@ -937,9 +937,11 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select_kernel(const KArgs a)
     if (a.topt & 16) {
       // fix-up mode: only the pixels qd_tunnel_select2_kernel marked (first key = QD_S2_MARK; item-level mark = a NaN in the
       // <n> scratch of the item's first pixel) are done here, each from a cold start
+      // (this launch uses shorter items than the marking kernel -- a.col_parts = its pixels per item -- so that an item
+      // whose pixels are all marked is shared by several warps)
       const long long pb = (long long)part * a.rows_per_item;
       if (pb >= (long long)gscan->nx * gscan->ny) continue;
-      const double fl = a.nbar[(gscan->pix_offset + pb) * N];
+      const double fl = a.nbar[(gscan->pix_offset + (pb / a.col_parts) * a.col_parts) * N];
       if (fl == fl) continue;
     }
     if (lane == 0) {
@@ -1321,10 +1323,11 @@ __global__ void __launch_bounds__(128, QD_TE_MIN_BLOCKS) qd_tunnel_eigen_kernel(
     const qd_scan* gscan = a.scans + scan_id;
     if (a.topt & 8) {
       // fix-up mode: qd_tunnel_eigen2_kernel left an item-level mark in the floor scratch of the item's first pixel (same
-      // item geometry in both launches); an item without a marked pixel is skipped before anything is staged
+      // item geometry in both launches); an item whose parent item holds no marked pixel is skipped before anything is staged
+      // (shorter items than the marking kernel's, a.col_parts = its pixels per item: see qd_tunnel_select_kernel)
       const long long pb = (long long)part * a.rows_per_item;
       if (pb >= (long long)gscan->nx * gscan->ny) continue;
-      if (a.tfloor[((size_t)scan_id * a.tstride + pb) * 8] != 0xff) continue;
+      if (a.tfloor[((size_t)scan_id * a.tstride + (pb / a.col_parts) * a.col_parts) * 8] != 0xff) continue;
     }
     if (lane == 0) {
       const int env = gscan->env_id;
