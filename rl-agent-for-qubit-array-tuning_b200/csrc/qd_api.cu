@@ -46,6 +46,8 @@ struct qd_ctx {
   size_t nbar_cap = 0;
   unsigned char* d_tfloor = nullptr;   // tunnel path, split pipeline: floor(n_c) of the current chunk, 8 bytes per pixel
   size_t tfloor_cap = 0;
+  double* d_tpot = nullptr;            // same chunk: dot potentials [8], tunnel couplings [7], cdd scale: 128 bytes per pixel
+  size_t tpot_cap = 0;
   unsigned long long* d_tkeys = nullptr;   // ... and its 32 kept basis states, 256 bytes per pixel
   size_t tkeys_cap = 0;
   void* d_obs = nullptr;          // qd_scan_obs_host: compact (typed) observation images before the copy-back
@@ -325,7 +327,10 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
       if (rc) return rc;
       rc = grow(ctx, &ctx->d_tkeys, &ctx->tkeys_cap, (size_t)spc * max_pix * 256);
       if (rc) return rc;
+      rc = grow(ctx, &ctx->d_tpot, &ctx->tpot_cap, (size_t)spc * max_pix * 128);
+      if (rc) return rc;
       g.tfloor = ctx->d_tfloor;
+      g.tpot = ctx->d_tpot;
       g.tkeys = ctx->d_tkeys;
       g.tstride = max_pix;
       for (long long c0 = 0; c0 < n_scan; c0 += spc) {
@@ -720,6 +725,7 @@ void qd_destroy(qd_ctx* ctx) {
   if (ctx->d_pts) cudaFree(ctx->d_pts);
   if (ctx->d_nbar) cudaFree(ctx->d_nbar);
   if (ctx->d_tfloor) cudaFree(ctx->d_tfloor);
+  if (ctx->d_tpot) cudaFree(ctx->d_tpot);
   if (ctx->d_tkeys) cudaFree(ctx->d_tkeys);
   if (ctx->d_obs) cudaFree(ctx->d_obs);
   if (ctx->d_stats) cudaFree(ctx->d_stats);

@@ -40,6 +40,7 @@ struct KArgs {
   // scans, addressed by (scan index inside the chunk) * tstride + pixel
   unsigned char* tfloor;               // [slots][8]   floor of the relaxed continuous occupations
   unsigned long long* tkeys;           // [slots][32]  the 32 kept basis states, 8 bits per dot
+  double* tpot;                        // [slots][16]  dot potentials g[0..8), tunnel couplings |t|[8..15), cdd scale s_c [15]
   long long tstride;                   // pixels per scan slot (largest scan of the upload)
   int topt;                            // tunnel path: optimisation switches (QDSIM_TUNNEL_OPT, default all on; A/B and bisection)
   float e2_kappa, e2_qsafe, e2_tol;    // qd_tunnel_eigen2_kernel: shift aggressiveness, contraction safety factor, stopping tolerance

@@ -839,12 +839,36 @@ __global__ void __launch_bounds__(128) qd_tunnel_relax_kernel(const KArgs a) {
         for (int j = 0; j < N; ++j) g[j] = fma(rec[L.o_a + j * NV + k], vk, g[j]);
       }
       double lr = 0.1;
+      double s_c = 1.0;
       if (vc_on) {
-        double s_c, sb;
+        double sb;
         vc_scales(par, vabs, v2, NV, s_c, sb);
 #pragma unroll
         for (int j = 0; j < N; ++j) g[j] *= sb;
         lr = 0.1 / s_c;
+      }
+      // the per-pixel quantities the select and eigen kernels need again (the same operations in the same order as their own
+      // former code): potentials, tunnel couplings t_d = |tc_base exp(-alpha_d vb_eff_d)|, scale of cdd
+      if (a.tpot) {
+        double* __restrict__ tp = a.tpot + ((size_t)scan_id * a.tstride + pix) * 16;
+#pragma unroll
+        for (int j = 0; j < N; ++j) tp[j] = g[j];
+        const int G = L.n_gate;
+        for (int d = 0; d < N - 1; ++d) {
+          double t = par[QD_PAR_TC_BASE];
+          if (NV > G) {
+            double vb = (a.points == nullptr) ? fma((double)iy, sc->dy[G + d], fma((double)ix, sc->dx[G + d], sc->v0[G + d]))
+                                              : a.points[(size_t)pix * NV + G + d];
+            for (int k = 0; k < G; ++k) {
+              const double vk = (a.points == nullptr) ? fma((double)iy, sc->dy[k], fma((double)ix, sc->dx[k], sc->v0[k]))
+                                                      : a.points[(size_t)pix * NV + k];
+              vb = fma(rec[L.o_cbg + d * G + k], vk, vb);
+            }
+            t *= exp(-rec[L.o_alpha + d] * vb);
+          }
+          tp[8 + d] = fabs(t);
+        }
+        tp[15] = s_c;
       }
       bool neg = false;
       double n[N];

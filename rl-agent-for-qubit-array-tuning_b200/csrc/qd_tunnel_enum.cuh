@@ -129,23 +129,10 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
       const int iy = (int)(pix / nx), ix = (int)(pix - (long long)iy * nx);
       const size_t tslot = (size_t)scan_id * a.tstride + pix;
       // ---------------- potentials, floor (from the relax kernel), r = f - g, rc = L^T r ----------------
-      if (lane < NV) {
-        vv[lane] = (a.points == nullptr) ? fma((double)iy, sc->dy[lane], fma((double)ix, sc->dx[lane], sc->v0[lane]))
-                                         : a.points[(size_t)pix * NV + lane];
-      }
       const uint64_t fk = *reinterpret_cast<const uint64_t*>(a.tfloor + tslot * 8);
-      __syncwarp();
-      if (lane < N) {
-        double acc = 0.0;
-        const double* arow = rec + L.o_a + lane * NV;
-        for (int k = 0; k < NV; ++k) acc = fma(arow[k], vv[k], acc);
-        if (vc_on) {
-          double vabs = 0.0;
-          for (int k = 0; k < NV; ++k) vabs += fabs(vv[k]);
-          acc *= fma(par[QD_PAR_VC_BETA], vabs / (double)NV, 1.0);          // (s_g is the same in every model)
-        }
+      if (lane < N) {                              // (the potentials come from the relax kernel)
         const double fj = (double)(unsigned)((fk >> (8 * lane)) & 0xffu);
-        rs[lane] = fj - acc;
+        rs[lane] = fj - a.tpot[tslot * 16 + lane];
       }
       __syncwarp();
       if (lane < N) {

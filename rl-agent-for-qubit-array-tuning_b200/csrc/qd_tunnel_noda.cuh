@@ -338,37 +338,15 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
         continue;
       }
       uint64_t key = a.tkeys[((size_t)scan_id * a.tstride + pix) * 32 + lane];
-      // ---------------- voltages, potentials, tunnel couplings ----------------
-      if (lane < NV) {
-        vv[lane] = (a.points == nullptr) ? fma((double)iy, sc->dy[lane], fma((double)ix, sc->dx[lane], sc->v0[lane]))
-                                         : a.points[(size_t)pix * NV + lane];
-      }
-      __syncwarp();
+      // ---------------- potentials, tunnel couplings, cdd scale: formed once per pixel by the relax kernel ----------------
       double s_c = 1.0;
-      if (lane < N) {
-        double acc = 0.0;
-        const double* arow = rec + L.o_a + lane * NV;
-        for (int k = 0; k < NV; ++k) acc = fma(arow[k], vv[k], acc);
-        if (vc_on) {
-          double vabs = 0.0, v2 = 0.0, s_g;
-          for (int k = 0; k < NV; ++k) { vabs += fabs(vv[k]); v2 = fma(vv[k], vv[k], v2); }
-          vc_scales(par, vabs, v2, NV, s_c, s_g);
-          acc *= s_g;
-        }
-        gs[lane] = acc;
-      }
-      if (lane >= 16 && lane < 16 + B) {
-        const int d = lane - 16;
-        double t = par[QD_PAR_TC_BASE];
-        if (barriers) {
-          double vb = vv[G + d];
-          for (int k = 0; k < G; ++k) vb = fma(rec[L.o_cbg + d * G + k], vv[k], vb);
-          t *= exp(-rec[L.o_alpha + d] * vb);
-        }
-        ts[d] = fabs(t);                            // the sign of t is a gauge (header)
+      {
+        const double* __restrict__ tp = a.tpot + ((size_t)scan_id * a.tstride + pix) * 16;
+        if (lane < N) gs[lane] = tp[lane];
+        if (lane >= 16 && lane < 16 + B) ts[lane - 16] = tp[8 + lane - 16];      // |t|: its sign is a gauge (header)
+        if (vc_on) s_c = tp[15];
       }
       __syncwarp();
-      if (vc_on) s_c = shfl_f64(s_c, 0);
       // ---------------- free energy of this lane's state (symmetric form: upper triangle once) ----------------
       int tc = 0;
       double Fm = 0.0;
