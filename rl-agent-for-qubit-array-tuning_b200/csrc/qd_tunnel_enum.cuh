@@ -22,8 +22,8 @@
 namespace qd {
 
 constexpr int QD_S2_CAP = 320;                    // nodes per level list (two lists); leaves share them
-// vv[16] gs[8] r[8] fs[8] rc[8] dd[8] | Lc[64] | listP[2][CAP] | listD[2][CAP] (u32) | outk[32] (u64)
-constexpr int QD_S2_SMALL = 56;
+// vv[16] gs[8] r[8] fs[8] rc[8] dd[8] Mt[72] | Lc[64] | listP[2][CAP] | listD[2][CAP] (u32) | outk[32] (u64)
+constexpr int QD_S2_SMALL = 56 + 72;                 // + Mt[8][9]: L^T with zeros below the diagonal (row k: L_jk, j > k)
 constexpr int QD_S2_WORK = QD_S2_SMALL + 64 + 2 * QD_S2_CAP + QD_S2_CAP + 32;
 constexpr unsigned long long QD_S2_MARK = 0xfffffffffffffffeULL;      // first key of a pixel left to the fix-up pass
 
@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
   double* fs = sv + 32;
   double* rc = sv + 40;             // rc_k = r_k + sum_{j>k} L_jk r_j
   double* dd = sv + 48;
+  double* Mt = sv + 56;             // Mt[k * 9 + j] = L_jk for j > k, else 0
   double* Lc = sv + QD_S2_SMALL;    // Lc[j * N + k] = L_jk (j > k)
   double* listP = Lc + 64;          // [2][CAP]
   unsigned* listD = reinterpret_cast<unsigned*>(listP + 2 * QD_S2_CAP);   // [2][CAP]
@@ -119,6 +120,11 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
       }
     }
     __syncwarp();
+    for (int e = lane; e < N * N; e += 32) {
+      const int k = e / N, j = e - k * N;
+      Mt[k * 9 + j] = (j > k) ? Lc[j * N + k] : 0.0;
+    }
+    __syncwarp();
     double dmin = dd[0];
 #pragma unroll
     for (int k = 1; k < N; ++k) dmin = fmin(dmin, dd[k]);
@@ -135,37 +141,42 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
         rs[lane] = fj - a.tpot[tslot * 16 + lane];
       }
       __syncwarp();
-      if (lane < N) {
-        double s = rs[lane];
-        for (int j = lane + 1; j < N; ++j) s = fma(Lc[j * N + lane], rs[j], s);
-        rc[lane] = s;
-        fs[lane] = s - Lc[lane * N + lane];           // rcm
-      }
-      __syncwarp();
       // dots whose floor is 0 lose the digit -1 (negative occupation: not a candidate)
       unsigned zero_floor = 0;
 #pragma unroll
       for (int j = 0; j < N; ++j) zero_floor |= (((fk >> (8 * j)) & 0xffu) == 0) ? (1u << j) : 0u;
-      // Lower bound of the terms still to come below level k, whatever the digits: y_j lies in an interval (digits in
-      // [lo, 2], interval arithmetic over the dots above j), term_j >= d_j dist(0, interval)^2.  Without it a deeply empty
-      // dot at the bottom of the tree (all of its digits cost ~tau) would leave the levels above it unpruned.
-      if (lane < N) {
-        double smin = 0.0, smax = 0.0;
-        for (int i = lane + 1; i < N; ++i) {
-          const double l = Lc[i * N + lane];
-          const double a0 = ((zero_floor >> i) & 1u) ? 0.0 : -l, a1 = 2.0 * l;
+      // rc, rcm, and the lower bound of the terms still to come below level k, whatever the digits: y_j lies in an interval
+      // (digits in [lo, 2], interval arithmetic over the dots above j), term_j >= d_j dist(0, interval)^2.  Without it a
+      // deeply empty dot at the bottom of the tree (all of its digits cost ~tau) would leave the levels above it unpruned.
+      // Lane k < N owns dot k; fixed trip counts on the zero-padded Mt (no serial single-lane stretches).
+      {
+        const int kk = min(lane, N - 1);
+        const double* __restrict__ mrow = Mt + kk * 9;
+        double sacc = rs[kk], smin = 0.0, smax = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const double l = mrow[j];
+          sacc = fma(l, rs[j], sacc);
+          const double a0 = ((zero_floor >> j) & 1u) ? 0.0 : -l, a1 = 2.0 * l;
           smin += fmin(a0, a1);
           smax += fmax(a0, a1);
         }
-        const double ylo = rc[lane] + (((zero_floor >> lane) & 1u) ? 0.0 : -1.0) + smin;
-        const double yhi = rc[lane] + 2.0 + smax;
+        const double ylo = sacc + (((zero_floor >> kk) & 1u) ? 0.0 : -1.0) + smin;
+        const double yhi = sacc + 2.0 + smax;
         const double dist = (ylo > 0.0) ? ylo : ((yhi < 0.0) ? -yhi : 0.0);
-        gs[lane] = dd[lane] * dist * dist * (1.0 - 1e-9);
-      }
-      __syncwarp();
-      if (lane == 0) {                              // rem[k] = sum_{j < k} bound_j
-        double acc = 0.0;
-        for (int k = 0; k < N; ++k) { const double t = gs[k]; gs[k] = acc; acc += t; }
+        const double bound = (lane < N) ? dd[kk] * dist * dist * (1.0 - 1e-9) : 0.0;
+        double incl = bound;                          // rem[k] = sum_{j < k} bound_j: exclusive scan over lanes 0..N-1
+#pragma unroll
+        for (int d = 1; d < N; d <<= 1) {
+          const double t = __hiloint2double(__shfl_up_sync(FULL, __double2hiint(incl), d),
+                                            __shfl_up_sync(FULL, __double2loint(incl), d));
+          if (lane >= d) incl += t;
+        }
+        if (lane < N) {
+          rc[lane] = sacc;
+          fs[lane] = sacc - Lc[lane * N + lane];      // rcm
+          gs[lane] = incl - bound;
+        }
       }
       __syncwarp();
       const double* __restrict__ rem = gs;
