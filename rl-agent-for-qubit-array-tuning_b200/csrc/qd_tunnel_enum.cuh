@@ -103,23 +103,34 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
     }
     const bool vc_on = par[QD_PAR_VC_ALPHA] != 0.0 || par[QD_PAR_VC_BETA] != 0.0;
 
-    // ---- per item: C = L D L^T (natural dot order) ----
-    if (lane == 0) {
-      double m[N][N];
-      for (int i = 0; i < N; ++i)
-        for (int j = 0; j < N; ++j) m[i][j] = C[i * N + j];
+    // ---- per item: C = L D L^T (natural dot order), the whole warp on the N x N entries (a single lane doing it
+    // serially showed up with 4.5 % of the kernel's stall samples) ----
+    {
+      double* __restrict__ W = listP;               // scratch: the lists are empty between items
+      for (int e = lane; e < N * N; e += 32) W[e] = C[e];
+      __syncwarp();
+#pragma unroll 1
       for (int k = 0; k < N; ++k) {
-        const double dk = m[k][k];
-        dd[k] = dk;
-        const double inv = 1.0 / dk;
-        double cs = 0.0;
-        for (int i = k + 1; i < N; ++i) { Lc[i * N + k] = m[i][k] * inv; cs += Lc[i * N + k]; }
-        Lc[k * N + k] = 1.0 + cs;                     // (diagonal slot: 1 + column sum, for rcm)
-        for (int i = k + 1; i < N; ++i)
-          for (int j = k + 1; j <= i; ++j) m[i][j] -= Lc[i * N + k] * m[j][k];
+        const double inv = 1.0 / W[k * N + k];
+        for (int e = lane; e < N * N; e += 32) {
+          const int i = e / N, j = e - i * N;
+          if (i > k && j > k && j <= i) W[e] = fma(-(W[i * N + k] * inv), W[j * N + k], W[e]);
+        }
+        __syncwarp();
       }
+      for (int e = lane; e < N * N; e += 32) {
+        const int i = e / N, k = e - i * N;
+        if (i > k) Lc[e] = W[e] / W[k * N + k];
+      }
+      if (lane < N) dd[lane] = W[lane * N + lane];
+      __syncwarp();
+      if (lane < N) {                               // (diagonal slot: 1 + column sum, for rcm)
+        double cs = 0.0;
+        for (int i = lane + 1; i < N; ++i) cs += Lc[i * N + lane];
+        Lc[lane * N + lane] = 1.0 + cs;
+      }
+      __syncwarp();
     }
-    __syncwarp();
     for (int e = lane; e < N * N; e += 32) {
       const int k = e / N, j = e - k * N;
       Mt[k * 9 + j] = (j > k) ? Lc[j * N + k] : 0.0;
@@ -131,14 +142,20 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
 
     uint64_t prev_key = ~0ULL;       // one of the previous pixel's 32 states (~0: none)
     bool any_marked = false;
+    // floor and potential of a pixel are fetched one pixel ahead (their latency was 5 % of the stall samples)
+    uint64_t fk_next = *reinterpret_cast<const uint64_t*>(a.tfloor + ((size_t)scan_id * a.tstride + p_begin) * 8);
+    double g_next = a.tpot[((size_t)scan_id * a.tstride + p_begin) * 16 + (lane & 7)];
     for (long long pix = p_begin; pix < p_end; ++pix) {
-      const int iy = (int)(pix / nx), ix = (int)(pix - (long long)iy * nx);
       const size_t tslot = (size_t)scan_id * a.tstride + pix;
       // ---------------- potentials, floor (from the relax kernel), r = f - g, rc = L^T r ----------------
-      const uint64_t fk = *reinterpret_cast<const uint64_t*>(a.tfloor + tslot * 8);
+      const uint64_t fk = fk_next;
       if (lane < N) {                              // (the potentials come from the relax kernel)
         const double fj = (double)(unsigned)((fk >> (8 * lane)) & 0xffu);
-        rs[lane] = fj - a.tpot[tslot * 16 + lane];
+        rs[lane] = fj - g_next;
+      }
+      if (pix + 1 < p_end) {
+        fk_next = *reinterpret_cast<const uint64_t*>(a.tfloor + (tslot + 1) * 8);
+        g_next = a.tpot[(tslot + 1) * 16 + (lane & 7)];
       }
       __syncwarp();
       // dots whose floor is 0 lose the digit -1 (negative occupation: not a candidate)

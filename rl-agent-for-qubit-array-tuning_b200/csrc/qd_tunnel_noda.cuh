@@ -330,21 +330,34 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
     bool any_fallback = false;
     __syncwarp();
 
+    // lane -> entry of the relax kernel's per-pixel record: potentials [0, 8) for the lanes below 16, couplings [8, 15)
+    // for lanes 16.., the cdd scale [15] for lane 31
+    const int tp_idx = (lane < 16) ? (lane & 7) : ((lane == 31) ? 15 : 8 + ((lane - 16) & 7));
+    uint64_t key_next = 0;
+    double tp_next = 0.0;
+    if (!replace) {
+      const size_t nslot = (size_t)scan_id * a.tstride + p_begin;
+      key_next = a.tkeys[nslot * 32 + lane];
+      tp_next = a.tpot[nslot * 16 + tp_idx];
+    }
     for (long long pix = p_begin; pix < p_end; ++pix) {
-      const int iy = (int)(pix / nx), ix = (int)(pix - (long long)iy * nx);
       double* const out = a.nbar + (pix0 + pix) * N;
       if (replace) {
         if (lane < N) out[lane] = 0.0;
         continue;
       }
-      uint64_t key = a.tkeys[((size_t)scan_id * a.tstride + pix) * 32 + lane];
+      uint64_t key = key_next;
       // ---------------- potentials, tunnel couplings, cdd scale: formed once per pixel by the relax kernel ----------------
       double s_c = 1.0;
       {
-        const double* __restrict__ tp = a.tpot + ((size_t)scan_id * a.tstride + pix) * 16;
-        if (lane < N) gs[lane] = tp[lane];
-        if (lane >= 16 && lane < 16 + B) ts[lane - 16] = tp[8 + lane - 16];      // |t|: its sign is a gauge (header)
-        if (vc_on) s_c = tp[15];
+        if (lane < N) gs[lane] = tp_next;
+        if (lane >= 16 && lane < 16 + B) ts[lane - 16] = tp_next;      // |t|: its sign is a gauge (header)
+        if (vc_on) s_c = shfl_f64(tp_next, 31);
+      }
+      if (pix + 1 < p_end) {                       // the next pixel's states and potentials, one pixel ahead
+        const size_t nslot = (size_t)scan_id * a.tstride + pix + 1;
+        key_next = a.tkeys[nslot * 32 + lane];
+        tp_next = a.tpot[nslot * 16 + tp_idx];
       }
       __syncwarp();
       // ---------------- free energy of this lane's state (symmetric form: upper triangle once) ----------------
