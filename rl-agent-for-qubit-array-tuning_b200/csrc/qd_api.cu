@@ -380,7 +380,8 @@ int launch(qd_ctx* ctx, int n_scan, const qd_scan* d_scans, int max_ny, const do
         const int fix_ppi = (ppi % 8 == 0) ? 8 : (int)ppi;          // (must divide the marking kernel's item length)
         const int fix_ips = (int)((max_pix + fix_ppi - 1) / fix_ppi);
         long long fix_grid = ((long long)nc * fix_ips + gw - 1) / gw;
-        if (fix_grid > 0x7fffffffLL) fix_grid = 0x7fffffffLL;
+        // (almost every item is skipped on its mark: a resident-size grid looping over the items instead of one CTA per four)
+        fix_grid = std::min<long long>(fix_grid, (long long)ctx->sm_count * 32);
         {
           qd::KArgs sa = g;
           long long sgrid = ggrid;
