@@ -133,9 +133,11 @@ class ChargeSensedDotArray:
                 if len(d["_affine_cache"]) > 64:
                     d["_affine_cache"].clear()
                 d["_affine_cache"][key] = aff
-        ng = self.n_gate
-        v0v, dxv, dyv = d["_scan1_views"]
-        v0v[:ng], dxv[:ng], dyv[:ng] = aff
+        if d.get("_scan1_aff") is not aff:          # (a cached sweep of physical gates: the descriptor already holds it)
+            ng = self.n_gate
+            v0v, dxv, dyv = d["_scan1_views"]
+            v0v[:ng], dxv[:ng], dyv[:ng] = aff
+            d["_scan1_aff"] = aff
         fl = d.get("_flags_cache")
         if fl is None or fl[0] != self._version:
             fl = d["_flags_cache"] = (self._version, self._flags(True))
@@ -150,7 +152,8 @@ class ChargeSensedDotArray:
             s["seed"] = fresh_seed()
         # hard argmin (T = 0): the occupations are small integers -- fetch them as one byte per dot (an eighth of the bytes
         # the kernel has to push over PCIe) and widen here; thermal averages come back as float64
-        z, n = engine_for(self, self.device).scan_one_host(s, N_F64 if flags & FLAG_THERMAL else N_U8, flags)
+        z, n = engine_for(self, self.device).scan_one_host(s, N_F64 if flags & FLAG_THERMAL else N_U8, flags,
+                                                           x_points * y_points)
         return (z.astype(np.float64).reshape(y_points, x_points, 1),
                 n.astype(np.float64).reshape(y_points, x_points, self.n_dot))
 

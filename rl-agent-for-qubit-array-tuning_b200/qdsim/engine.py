@@ -137,6 +137,7 @@ class Engine:
             raise QdError(rc, self._lib.qd_last_error(None).decode())
         self.device = int(device)
         self.models: ModelBatch | None = None
+        self._one_bufs: dict = {}           # staging buffers of scan_one_host, by (pixels, n_type)
 
     # -- lifecycle -------------------------------------------------------------------------------------------
     def close(self):
@@ -212,17 +213,29 @@ class Engine:
         self._check(self._lib.qd_scan_open_host(self._ctx, len(scans), _ptr(scans), _ptr(z), _ptr(n), n_type, flags))
         return z, n
 
-    def scan_one_host(self, scan: np.ndarray, n_type: int = N_F64, flags: int = 0):
+    def scan_one_host(self, scan: np.ndarray, n_type: int = N_F64, flags: int = 0, pixels: int | None = None):
         """One scan window (a single ``do2d_open``), minimal host overhead: ``scan`` is a 1-element ``SCAN_DTYPE`` array with
-        ``pix_offset == 0``; returns fresh ``(z float32 [ny * nx], n [ny * nx, N])``.  The library takes its single-scan
-        path: descriptor in the kernel parameters, outputs written straight into mapped pinned memory, one sync."""
-        pixels = int(scan["nx"][0]) * int(scan["ny"][0])
-        z = np.empty(pixels, dtype=np.float32)
-        n = np.empty((pixels, self.models.n_dot), dtype=N_DTYPES[n_type])
-        rc = self._lib.qd_scan_open_host(self._ctx, 1, scan.ctypes.data, z.ctypes.data, n.ctypes.data, n_type, flags)
+        ``pix_offset == 0``; returns ``(z float32 [ny * nx], n [ny * nx, N])`` -- views of per-engine staging buffers that the
+        NEXT call overwrites (the drop-in class widens them to fresh float64 arrays).  ``pixels`` = ny * nx if the caller has
+        it at hand (reading it back from the record costs a microsecond).  The library takes its single-scan path:
+        descriptor in the kernel parameters, outputs written straight into mapped pinned memory, one sync."""
+        if pixels is None:
+            pixels = int(scan["nx"][0]) * int(scan["ny"][0])
+        key = (pixels, n_type)
+        buf = self._one_bufs.get(key)
+        if buf is None:
+            if len(self._one_bufs) > 16:
+                self._one_bufs.clear()
+            z = np.empty(pixels, dtype=np.float32)
+            n = np.empty((pixels, self.models.n_dot), dtype=N_DTYPES[n_type])
+            buf = self._one_bufs[key] = (z, n, z.ctypes.data, n.ctypes.data, self.models.n_dot)
+        if buf[4] != self.models.n_dot:
+            self._one_bufs.clear()
+            return self.scan_one_host(scan, n_type, flags, pixels)
+        rc = self._lib.qd_scan_open_host(self._ctx, 1, scan.ctypes.data, buf[2], buf[3], n_type, flags)
         if rc != 0:
             self._check(rc)
-        return z, n
+        return buf[0], buf[1]
 
     def scan_obs_host(self, scans: np.ndarray, z_type: int = Z_U8, flags: int = 0, normalise: bool = True,
                       q_low: float = 0.5, q_high: float = 99.5, out: np.ndarray | None = None, want_stats: bool = False,
