@@ -22,13 +22,13 @@
 namespace qd {
 
 constexpr int QD_S2_CAP = 320;                    // nodes per level list (two lists); leaves share them
-// vv[16] gs[8] r[8] fs[8] rc[8] dd[8] Mt[72] | Lc[64] | listP[2][CAP] | listD[2][CAP] (u32) | outk[32] (u64)
+// (16 spare) rem[8] r[8] rcm[8] rc[8] dd[8] Mt[72] | Lc[64] | listP[2][CAP] | listD[2][CAP] (u32) | outk[32] (u64)
 constexpr int QD_S2_SMALL = 56 + 72;                 // + Mt[8][9]: L^T with zeros below the diagonal (row k: L_jk, j > k)
 constexpr int QD_S2_WORK = QD_S2_SMALL + 64 + 2 * QD_S2_CAP + QD_S2_CAP + 32;
 constexpr unsigned long long QD_S2_MARK = 0xfffffffffffffffeULL;      // first key of a pixel left to the fix-up pass
 
-__host__ __device__ inline int qd_tunnel_select2_slot_bytes(const qd_layout& L) {
-  return (L.gs_doubles * 8 + (int)sizeof(qd_scan) + QD_S2_WORK * 8 + 16 + 127) & ~127;
+__host__ __device__ inline int qd_tunnel_select2_slot_bytes(const qd_layout&) {
+  return (QD_S2_WORK * 8 + 127) & ~127;
 }
 
 // One term of the energy, the same rounded operations wherever it is formed.  Digits enter as codes c = delta + 1 in
@@ -39,23 +39,20 @@ __device__ __forceinline__ double s2_term(double rcm_k, double s, double code, d
 }
 
 template <int N>
-__global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a) {
+__global__ void __launch_bounds__(128, 5) qd_tunnel_select2_kernel(const KArgs a) {
   constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char qd_smem[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const qd_layout& L = a.L;
-  const int NV = L.n_volt;
 
-  unsigned char* slot = qd_smem + (size_t)warp * a.slot_bytes;
-  double* rec = reinterpret_cast<double*>(slot);
-  qd_scan* sc = reinterpret_cast<qd_scan*>(slot + (size_t)L.gs_doubles * 8);
-  double* sv = reinterpret_cast<double*>(slot + (size_t)L.gs_doubles * 8 + sizeof(qd_scan));
-  double* vv = sv;
-  double* gs = sv + 16;
+  // nothing is staged: the potentials come from the relax kernel, cdd_inv is read once per item for the factorisation,
+  // the four scalars of the scan descriptor straight from global memory (9.5 KB per warp -> five CTAs per SM)
+  double* sv = reinterpret_cast<double*>(qd_smem + (size_t)warp * a.slot_bytes);
+  double* gs = sv + 16;             // rem[k]: lower bound of the levels below k
   double* rs = sv + 24;             // r = floor - g
-  double* fs = sv + 32;
+  double* fs = sv + 32;             // rcm
   double* rc = sv + 40;             // rc_k = r_k + sum_{j>k} L_jk r_j
   double* dd = sv + 48;
   double* Mt = sv + 56;             // Mt[k * 9 + j] = L_jk for j > k, else 0
@@ -63,14 +60,7 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
   double* listP = Lc + 64;          // [2][CAP]
   unsigned* listD = reinterpret_cast<unsigned*>(listP + 2 * QD_S2_CAP);   // [2][CAP]
   uint64_t* outk = reinterpret_cast<uint64_t*>(listP + 2 * QD_S2_CAP + QD_S2_CAP);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sv + QD_S2_WORK);
-  const double* __restrict__ C = rec + L.o_cinv;
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
-
-  if (lane == 0) mbar_init(bar, 1);
-  __syncwarp();
-  uint32_t phase = 0;
-  const uint32_t rec_bytes = (uint32_t)L.gs_doubles * 8u;
 
   const long long total_items = (long long)a.n_scan * a.items_per_scan;
   for (long long item = (long long)blockIdx.x * warps_per_cta + warp; item < total_items;
@@ -78,30 +68,19 @@ __global__ void __launch_bounds__(128, 4) qd_tunnel_select2_kernel(const KArgs a
     const int scan_id = (int)(item / a.items_per_scan);
     const int part = (int)(item - (long long)scan_id * a.items_per_scan);
     const qd_scan* gscan = a.scans + scan_id;
-    if (lane == 0) {
-      const int env = gscan->env_id;
-      fence_proxy_async();
-      mbar_expect_tx(bar, rec_bytes + (uint32_t)sizeof(qd_scan));
-      tma_bulk_g2s(rec, a.records + (size_t)env * L.rec_doubles, rec_bytes, bar);
-      tma_bulk_g2s(sc, gscan, (uint32_t)sizeof(qd_scan), bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-
-    const int nx = sc->nx, ny = sc->ny;
+    const int nx = gscan->nx, ny = gscan->ny;
     const long long npix = (long long)nx * ny;
     const long long p_begin = (long long)part * a.rows_per_item;
     const long long p_end = min(npix, p_begin + (long long)a.rows_per_item);
-    if (p_begin >= npix) { __syncwarp(); continue; }
-    const double* par = rec + L.o_par;
-    const bool replace = (a.flags & QD_FLAG_RADIAL) && sc->rad_mode == 2;
-    const long long pix0 = sc->pix_offset;
+    if (p_begin >= npix) continue;
+    const bool replace = (a.flags & QD_FLAG_RADIAL) && gscan->rad_mode == 2;
+    const long long pix0 = gscan->pix_offset;
     if (replace) {
       if (lane == 0) a.nbar[(pix0 + p_begin) * N] = 0.0;
-      __syncwarp();
       continue;
     }
-    const bool vc_on = par[QD_PAR_VC_ALPHA] != 0.0 || par[QD_PAR_VC_BETA] != 0.0;
+    const double* __restrict__ C = a.records + (size_t)gscan->env_id * L.rec_doubles + L.o_cinv;
+    __syncwarp();
 
     // ---- per item: C = L D L^T (natural dot order), the whole warp on the N x N entries (a single lane doing it
     // serially showed up with 4.5 % of the kernel's stall samples) ----

@@ -26,15 +26,18 @@
 namespace qd {
 
 constexpr int QD_E2_LS = 17;                         // row stride of the sector-local matrices (odd: conflict free)
-constexpr int QD_E2_CB = 48;                         // one pivot-column buffer (lane + 15 stays inside)
-// H17 | Lm (vv[16] gs[8] ts[8] alias its head: they are dead before the first factorisation) | colbuf[2][48] (the
-// start vector of the first mat-vec and the sort permutation alias it) | hash keys[64] | hash x[64]
-constexpr int QD_E2_PAD = 48;                        // see e2_factor_sm
-constexpr int QD_E2_WORK = 2 * 32 * QD_E2_LS + 2 * QD_E2_CB + 128 + QD_E2_PAD;
+// Shared memory per warp: cinv[N^2] | Lm[32][17] | H17[32][17] | hash keys[64] | hash x[64].  Nothing else is staged: the
+// per-pixel potentials come from the relax kernel, the four scalars of the scan descriptor are read from global memory.
+// Lm comes FIRST: the loops of the factorisation run to a warp-uniform bound and read up to 271 doubles past a short
+// sector's rows -- with this order they land in H17 (finite numbers), and no padding is needed.  Small per-pixel vectors
+// alias the head of Lm (dead before the first factorisation): gs[8] at +16, ts[8] at +24, the sort permutation at +32,
+// the start vector of the first mat-vec at +64 (48 entries).  10.1 KB at 8 dots -> five CTAs of four warps per SM.
+constexpr int QD_E2_WORK = 2 * 32 * QD_E2_LS + 128;
 constexpr int QD_E2_MAXIT = 12;
 
 __host__ __device__ inline int qd_tunnel_eigen2_slot_bytes(const qd_layout& L) {
-  return (L.gs_doubles * 8 + (int)sizeof(qd_scan) + QD_E2_WORK * 8 + 16 + 127) & ~127;
+  const int cinv_doubles = (L.n_dot * L.n_dot + 1) & ~1;
+  return ((cinv_doubles + QD_E2_WORK) * 8 + 127) & ~127;
 }
 
 // 1 / x for a positive normal x: MUFU.RCP64H seed (20 bits) + two Newton steps
@@ -118,94 +121,16 @@ __device__ __forceinline__ double warp_max_rx(double v) {
   return ord_val(((unsigned long long)mh << 32) | ml);
 }
 
-// LDL^T of (A - sig I) for every sector at once.  Lane = row; the row is loaded into registers (the diagonal entry is
-// tracked apart in `d`); at step k every lane publishes its entry of column k, reads the pivot and the column back
-// (broadcast inside a sector).  `mact` (warp uniform) = size of the largest sector that matters: steps and column groups
-// beyond it are skipped.  Returns "my own pivot was not positive".  Rows of L go to lrow (entries c < ri; zero beyond),
-// 1 / d_i to dinv.  ONE instantiation on purpose: the kernel is bound by instruction fetch as soon as its hot code
-// outgrows the 32 KB instruction cache (measured: four unrolled sizes -> 5.5 no-instruction stall cycles per issue).
-__device__ __forceinline__ bool e2_factor(const double* __restrict__ hrow, double* __restrict__ lrow, double* __restrict__ colbuf,
-                                          int lane, int s0, int ri, double d, double pfloor, double& dinv, int mact) {
-  double a[16];
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (4 * g < mact) {
-#pragma unroll
-      for (int c = 4 * g; c < 4 * g + 4; ++c) a[c] = hrow[c];
-    } else {
-#pragma unroll
-      for (int c = 4 * g; c < 4 * g + 4; ++c) a[c] = 0.0;
-    }
-  }
-  bool fail = false;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    if (k < mact) {
-      double* buf = colbuf + (k & 1) * QD_E2_CB;
-      const double ak = a[k];
-      buf[lane] = (ri == k) ? d : ak;
-      __syncwarp();
-      const double* __restrict__ col = buf + s0;
-      double piv = col[k];
-      const bool ok = piv > pfloor;
-      if (ri == k) fail = !ok;
-      piv = ok ? piv : pfloor;
-      const double inv = rcp_nr(piv);
-      if (ri == k) dinv = inv;
-      const double l = (ri > k) ? ak * inv : 0.0;
-      d = fma(-l, ak, d);
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (4 * g + 3 > k && 4 * g < mact) {
-#pragma unroll
-          for (int c = 4 * g; c < 4 * g + 4; ++c)
-            if (c > k) a[c] = fma(-l, col[c], a[c]);
-        }
-      }
-      a[k] = l;
-    }
-  }
-#pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    if (4 * g < mact) {
-#pragma unroll
-      for (int c = 4 * g; c < 4 * g + 4; ++c) lrow[c] = a[c];
-    }
-  }
-  return fail;
-}
-
-// y = (L D L^T)^-1 x by forward / diagonal / backward substitution; valid for the sectors with m <= mact.  Rolled loops
-// (code size, see above); the chain of dependent shuffles bounds it either way.
-__device__ __forceinline__ double e2_solve(const double* __restrict__ Lm, int lane, int s0, int ri, int m, double dinv, double x,
-                                           int mact) {
-  const double* __restrict__ lrow = Lm + lane * QD_E2_LS;
-  double y = x;
-#pragma unroll 2
-  for (int k = 0; k + 1 < mact; ++k) {
-    const double yk = shfl_f64(y, min(s0 + k, 31));
-    const double l = lrow[k];
-    if (ri > k) y = fma(-l, yk, y);
-  }
-  y *= dinv;
-#pragma unroll 2
-  for (int k = mact - 1; k >= 1; --k) {
-    const int src = min(s0 + k, 31);
-    const double yk = shfl_f64(y, src);
-    const double l = Lm[src * QD_E2_LS + ri];
-    if (ri < k && k < m) y = fma(-l, yk, y);
-  }
-  return y;
-}
-
-// ---- compact alternative (QD_E2_SMEM_FACTOR): the factorisation in place in shared memory, rolled loops.  ~15 % more
-// instructions per factorisation than the register form above, a tenth of its code.  W[i][k] (i > k) keeps
-// l_ik d_k; the substitutions scale by 1 / d_k on the fly.
+// LDL^T of (A - sig I) for every sector at once, in place in shared memory, rolled loops: lane = row.  W[i][k] (i > k)
+// keeps l_ik d_k; the substitutions scale by 1 / d_k on the fly.  (A form with the rows in registers needs static
+// indexing, i.e. full unrolling for every size: ~15 % fewer instructions per factorisation, ten times the code -- the
+// kernel was then bound by instruction fetch)  `mact` (warp uniform) = size of the largest
+// sector that matters.  Returns "my own pivot was not positive"; 1 / d_i goes to dinv.
 __device__ __forceinline__ bool e2_factor_sm(const double* __restrict__ hrow, double* W, int lane, int s0, int ri, double d,
                                              double pfloor, double& dinv, int mact) {
   // Loops run to the warp-uniform mact without clamps: a sector shorter than mact reads rows past its end (other
-  // sectors' rows, or -- past lane 31 -- the buffers behind W and the QD_E2_PAD doubles that follow them) into columns at
-  // or beyond its own size, which nothing reads back.
+  // sectors' rows, or -- past lane 31 -- the H17 matrix that follows W in shared memory) into columns at or beyond its
+  // own size, which nothing reads back.
   double* wrow = W + lane * QD_E2_LS;
 #pragma unroll 4
   for (int c = 0; c < mact; ++c) wrow[c] = hrow[c];
@@ -257,7 +182,7 @@ __device__ __forceinline__ double e2_solve_sm(const double* __restrict__ W, int 
 }
 
 #ifndef QD_E2_MIN_BLOCKS
-#define QD_E2_MIN_BLOCKS 4
+#define QD_E2_MIN_BLOCKS 5
 #endif
 template <int N>
 __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel(const KArgs a) {
@@ -270,32 +195,20 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
   const int warp = threadIdx.x >> 5;
   const int warps_per_cta = blockDim.x >> 5;
   const qd_layout& L = a.L;
-  const int NV = L.n_volt, G = L.n_gate;
-  const bool barriers = NV > G;
   for (int k = threadIdx.x; k < 258; k += blockDim.x) sq_tab[k] = sqrt((double)k);
   __syncthreads();
 
-  unsigned char* slot = qd_smem + (size_t)warp * a.slot_bytes;
-  double* rec = reinterpret_cast<double*>(slot);
-  qd_scan* sc = reinterpret_cast<qd_scan*>(slot + (size_t)L.gs_doubles * 8);
-  double* wk = reinterpret_cast<double*>(slot + (size_t)L.gs_doubles * 8 + sizeof(qd_scan));
-  double* H = wk;                                   // [32][17]: row `lane`, columns of the lane's own sector
-  double* Lm = H + 32 * QD_E2_LS;                   // [32][17]: rows of L
-  double* vv = Lm;                                  // (dead before the first factorisation)
-  double* gs = vv + 16;
-  double* ts = gs + 8;
-  double* colbuf = Lm + 32 * QD_E2_LS;              // [2][48]
-  uint64_t* hkey = reinterpret_cast<uint64_t*>(colbuf + 2 * QD_E2_CB);   // [64]
+  constexpr int CINV_DOUBLES = (N * N + 1) & ~1;
+  double* Csm = reinterpret_cast<double*>(qd_smem + (size_t)warp * a.slot_bytes);
+  double* Lm = Csm + CINV_DOUBLES;                  // [32][17]: the factorisation, in place
+  double* H = Lm + 32 * QD_E2_LS;                   // [32][17]: row `lane`, columns of the lane's own sector
+  double* gs = Lm + 16;                             // (aliases, dead before the first factorisation: see QD_E2_WORK)
+  double* ts = Lm + 24;
+  int* perm = reinterpret_cast<int*>(Lm + 32);
+  double* colbuf = Lm + 64;                         // start vector of the first mat-vec, [48]
+  uint64_t* hkey = reinterpret_cast<uint64_t*>(H + 32 * QD_E2_LS);       // [64]
   double* hx = reinterpret_cast<double*>(hkey + 64);                     // [64]
-  for (int i = lane; i < QD_E2_PAD; i += 32) hx[64 + i] = 0.0;
-  uint64_t* bar = reinterpret_cast<uint64_t*>(wk + QD_E2_WORK);
-  const double* __restrict__ C = rec + L.o_cinv;
-
-  if (lane == 0) mbar_init(bar, 1);
-  if (lane < 16) { colbuf[32 + lane] = 0.0; colbuf[QD_E2_CB + 32 + lane] = 0.0; }   // the pads a lane past 31 reads
-  __syncwarp();
-  uint32_t phase = 0;
-  const uint32_t rec_bytes = (uint32_t)L.gs_doubles * 8u;
+  const double* __restrict__ C = Csm;
 
   const long long total_items = (long long)a.n_scan * a.items_per_scan;
   for (long long item = (long long)blockIdx.x * warps_per_cta + warp; item < total_items;
@@ -303,25 +216,17 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
     const int scan_id = (int)(item / a.items_per_scan);
     const int part = (int)(item - (long long)scan_id * a.items_per_scan);
     const qd_scan* gscan = a.scans + scan_id;
-    if (lane == 0) {
-      const int env = gscan->env_id;
-      fence_proxy_async();
-      mbar_expect_tx(bar, rec_bytes + (uint32_t)sizeof(qd_scan));
-      tma_bulk_g2s(rec, a.records + (size_t)env * L.rec_doubles, rec_bytes, bar);
-      tma_bulk_g2s(sc, gscan, (uint32_t)sizeof(qd_scan), bar);
-    }
-    mbar_wait(bar, phase);
-    phase ^= 1u;
-
-    const int nx = sc->nx, ny = sc->ny;
+    const int nx = gscan->nx, ny = gscan->ny;
     const long long npix = (long long)nx * ny;
     const long long p_begin = (long long)part * a.rows_per_item;
     const long long p_end = min(npix, p_begin + (long long)a.rows_per_item);
-    if (p_begin >= npix) { __syncwarp(); continue; }
-    const double* par = rec + L.o_par;
-    const bool replace = (a.flags & QD_FLAG_RADIAL) && sc->rad_mode == 2;
-    const long long pix0 = sc->pix_offset;
-    const bool vc_on = par[QD_PAR_VC_ALPHA] != 0.0 || par[QD_PAR_VC_BETA] != 0.0;
+    if (p_begin >= npix) continue;
+    const double* __restrict__ grec = a.records + (size_t)gscan->env_id * L.rec_doubles;
+    __syncwarp();
+    for (int e = lane; e < N * N; e += 32) Csm[e] = grec[L.o_cinv + e];
+    const bool replace = (a.flags & QD_FLAG_RADIAL) && gscan->rad_mode == 2;
+    const long long pix0 = gscan->pix_offset;
+    const bool vc_on = grec[L.o_par + QD_PAR_VC_ALPHA] != 0.0 || grec[L.o_par + QD_PAR_VC_BETA] != 0.0;
 
     // warm start across the pixels of the item: (basis state -> vector entry) of the previous pixel, gap estimate
     hkey[lane] = ~0ULL;
@@ -395,7 +300,6 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
           if (v < tc) rank += __popc(grp);
           rem &= ~grp;
         }
-        int* perm = reinterpret_cast<int*>(colbuf + QD_E2_CB);
         perm[rank] = lane;
         __syncwarp();
         const int src = perm[lane];
@@ -465,6 +369,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
         }
         x = fmax(x, 1e-3);
         colbuf[lane] = x;
+        if (lane < 16) colbuf[32 + lane] = 0.0;          // (what a lane of the last sectors reads past lane 31)
         __syncwarp();
         double w = 0.0;
         {
@@ -518,11 +423,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
           const int mact = __reduce_max_sync(FULL, act ? m : 0);
           if (need_fac) {
             if (test && live) sig = U;
-#ifndef QD_E2_REG_FACTOR
             const bool fl = e2_factor_sm(hrow, Lm, lane, s0, ri, Fm - sig, pfloor, dinv, mact);
-#else
-            const bool fl = e2_factor(hrow, Lm + lane * QD_E2_LS, colbuf, lane, s0, ri, Fm - sig, pfloor, dinv, mact);
-#endif
             const unsigned fm = __ballot_sync(FULL, fl);
             valid = (m <= mact) && !(fm & seg);
             __syncwarp();
@@ -532,11 +433,7 @@ __global__ void __launch_bounds__(128, QD_E2_MIN_BLOCKS) qd_tunnel_eigen2_kernel
           st_aggfail += __any_sync(FULL, act && !test && !valid && agg);
           st_testfail += __any_sync(FULL, act && test && !valid);
 #endif
-#ifndef QD_E2_REG_FACTOR
           double y = e2_solve_sm(Lm, lane, s0, ri, m, dinv, x, mact);
-#else
-          double y = e2_solve(Lm, lane, s0, ri, m, dinv, x, mact);
-#endif
           const bool usable = valid && m <= mact && m > 1;
           if (!usable) y = x;
           const double ny2 = seg_sum16(y * y, lane, s0, s1);
